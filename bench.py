@@ -1,0 +1,398 @@
+#!/usr/bin/env python
+"""bench.py — ocean tile-frames/s of the wave-synthesis hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c3|c4]
+
+A "step" = one batch of tile-frames through ComputeWaves (K1 evolve+transform, K2 transform+pack, K3 normalise).
+Default workload = BASELINE.json configs[1]: 1024x1024 tile, animation frames t_i = i*0.05 s (1000 frames =
+10 steps x 100 frames).  Under torchrun every rank owns one GPU and processes its own frames (frames are
+independent: weak scaling, no data-path collective); the timed region is bracketed by barrier + synchronize and
+the reported time is the max over ranks.  Rank 0 prints ONE JSON line.
+
+  value     device-resident throughput (maps stay in HBM, 100 distinct output slots = 3.4 GB per step >> L2)
+  e2e       same metric through the reference-facing C-ABI call with HOST output buffers (pinned), D2H inside
+  roofline  dominant kernel: algorithmic bytes / CUDA-event duration vs the measured HBM peak
+  cpu_baseline  the reference's own CPU code (oracle/_ref) or its restatement, timed on this box's host cores
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# algorithmic bytes per grid point per tile-frame of THIS design: K1 reads h0 (amp 8 + omega 4)
+# and writes the Hermitian-packed intermediate (4 fields x 4 B); K2 reads it and writes both RGBA32F maps;
+# K3 reads+writes disp.y.  (SURVEY.md §8d's two-pass model of a 7-field C2R design is 40 / 60 / 8 = 108.)
+BYTES_PER_POINT = {"K1": 28.0, "K2": 48.0, "K3": 8.0}
+SURVEY_BYTES_PER_POINT = {"K1": 40.0, "K2": 60.0, "K3": 8.0}
+
+WORKLOADS = {
+    # name: (N, tile_length, seed, frames per step, tiles, description)
+    "c1": dict(n=512, L=1000.0, seed=1234, frames=1, tiles=1, dt=1.5,
+               desc="BASELINE configs[0]: default 512x512 tile, single timestep per step"),
+    "c2": dict(n=1024, L=2000.0, seed=1, frames=100, tiles=1, dt=0.05,
+               desc="BASELINE configs[1]: 1024x1024 tile animated, t_i = i*0.05 s, 100 frames per step"),
+    "c3": dict(n=2048, L=4000.0, seed=2, frames=32, tiles=1, dt=0.05,
+               desc="BASELINE configs[2]: 2048x2048 tile, all maps, frames t_i = i*0.05 s, 32 frames per step per GPU"),
+    "c4": dict(n=512, L=1000.0, seed=1000, frames=64, tiles=64, dt=0.0,
+               desc="BASELINE configs[3]: 64 independent 512x512 tiles (wind angle 2*pi*j/64, V=5+0.5j, seed 1000+j), t=10"),
+}
+
+
+def gauss(n, seed):
+    rng = np.random.default_rng(seed)
+    return (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))).astype(np.complex64)
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------------
+def cpu_reference_model(wl, fft_fast=True):
+    """The reference's CPU implementation of the path: oracle/_ref when it was compiled (kind 'reference'),
+    else the C++ restatement (kind 'port').  Returns (kind, label, cores, prepare(tile)->callable(t))."""
+    from oracle import port as P
+    from oracle import refmodel as R
+    n, L = wl["n"], wl["L"]
+    if R.available():
+        mode = R.FFT_FLOAT32
+        label = "reference WSTessendorf.cpp verbatim + shim fp32 FFT (NOT FFTW)"
+        try:
+            if R.lib().wsref_set_fft_mode(R.FFT_REAL_FFTW) == 0:
+                mode, label = R.FFT_REAL_FFTW, "reference WSTessendorf.cpp verbatim + libfftw3f.so.3"
+        except Exception:
+            pass
+        cores = R.max_threads()
+
+        def make(tile):
+            m = R.RefWSTessendorf(n, L, fft_mode=mode)
+            prm = tile_params(wl, tile)
+            m.SetWindDirection(prm["wind"][0], prm["wind"][1])
+            m.SetWindSpeed(prm["speed"])
+            m.PrepareWithGauss(gauss(n, wl["seed"] + tile))
+            return m.ComputeWaves
+        return "reference", label, cores, make
+    cores = int(P.lib().wso_oracle_max_threads())
+
+    def make(tile):
+        prm = tile_params(wl, tile)
+        o = P.PortOracle(P.OceanParams(tile_size=n, tile_length=L, wind_x=prm["wind"][0], wind_y=prm["wind"][1],
+                                       wind_speed=prm["speed"]))
+        o.prepare(gauss(n, wl["seed"] + tile))
+        return lambda t: o.compute_waves(t, fft_mode=1)[0]
+    return "port", "C++ restatement oracle/ws_oracle.cpp + fp32 FFT (NOT FFTW)", cores, make
+
+
+def tile_params(wl, j):
+    if wl["tiles"] == 1:
+        return dict(wind=(1.0, 1.0), speed=30.0)
+    ang = 2.0 * np.pi * j / wl["tiles"]
+    return dict(wind=(float(np.cos(ang)), float(np.sin(ang))), speed=5.0 + 0.5 * j)
+
+
+def step_times(wl, step):
+    f = wl["frames"]
+    if wl["tiles"] > 1:
+        return np.full(f, 10.0, np.float32), np.arange(f, dtype=np.uint32) % wl["tiles"]
+    i0 = step * f
+    return (np.arange(i0, i0 + f, dtype=np.float32) * np.float32(wl["dt"])), None
+
+
+def run_reference_arm(args, wl, rank, world):
+    if rank != 0:
+        return
+    kind, label, cores, make = cpu_reference_model(wl)
+    # bounded sample per step so the whole run ends within minutes
+    sample = {512: 8, 1024: 3, 2048: 1}.get(wl["n"], 1)
+    fns = [make(j) for j in range(min(wl["tiles"], sample))]
+    def one_step(k):
+        t, tl = step_times(wl, k)
+        for i in range(sample):
+            fns[i % len(fns)](float(t[i % len(t)]))
+    for k in range(args.warmup):
+        one_step(k)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        one_step(args.warmup + k)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "ocean tile-frames/s", "value": value, "unit": "tile-frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "tile_size": wl["n"], "frames_per_step": sample,
+                   "note": "CPU arm: each step is a bounded sample of the workload's frames; rank 0 only"},
+        "cpu_baseline": {"value": value, "unit": "tile-frames/s", "cores": cores, "kind": kind,
+                         "sample": f"{sample} x {wl['n']}^2 tile-frames per step, {label}"},
+        "e2e": {"value": value, "unit": "tile-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def measure_cpu_baseline(wl, budget_s=12.0):
+    kind, label, cores, make = cpu_reference_model(wl)
+    fn = make(0)
+    t, _ = step_times(wl, 0)
+    fn(float(t[0]))  # warm-up (first-touch, thread pool)
+    t0 = time.perf_counter()
+    fn(float(t[-1]))
+    one = time.perf_counter() - t0
+    nfr = int(max(3, min(200, budget_s / max(one, 1e-4))))
+    t0 = time.perf_counter()
+    for i in range(nfr):
+        fn(float(t[i % len(t)]))
+    dt = time.perf_counter() - t0
+    return {"value": nfr / dt, "unit": "tile-frames/s", "cores": cores, "kind": kind,
+            "ms_per_tile_frame": dt / nfr * 1e3,
+            "sample": f"{nfr} ComputeWaves(t) calls at {wl['n']}^2 after 1 warm-up, {label}"}
+
+
+# ----------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-frames", type=int, default=0, help="tile-frames per e2e step (default: min(frames, 24))")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    wl = dict(WORKLOADS[args.workload])
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, wl, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import watersurfacerendering_b200 as W
+    from watersurfacerendering_b200 import sharding
+
+    n, F = wl["n"], wl["frames"]
+    ws = W.WSTessendorf(n, wl["L"], device=local_rank, max_tiles=wl["tiles"], max_slots=max(F, 2))
+    for j in range(wl["tiles"]):
+        prm = tile_params(wl, j)
+        ws.SetWindDirection(prm["wind"], j)
+        ws.SetWindSpeed(prm["speed"], j)
+        # every rank owns its own realisation (independent tiles / its share of the animation)
+        ws.PrepareWithGauss(gauss(n, wl["seed"] + j + 7919 * rank), tile=j)
+    stream = torch.cuda.current_stream()
+    ws.set_stream(stream.cuda_stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run_steps(first, count):
+        for k in range(first, first + count):
+            t, tl = step_times(wl, k)
+            ws.compute_batch(t, tiles=tl, first_slot=0)
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        tt = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    # ---- device-resident throughput -------------------------------------------------------------
+    run_steps(0, args.warmup)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = ws.stats()["kernel_launches"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    run_steps(args.warmup, args.steps)
+    e1.record(stream)
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = ws.stats()["kernel_launches"] - l0
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * F * args.steps / (ms * 1e-3)
+
+    # ---- per-kernel timing (same steps again, CUDA events around every launch) -----------------------
+    ws.set_profiling(True)
+    run_steps(args.warmup, args.steps)
+    prof = ws.profile()
+    ws.set_profiling(False)
+    names = ["K1", "K2", "K3"]
+    kms = prof["ms"]
+    dom = int(np.argmax(kms))
+    peak, peak_src = measured_peak()
+    pts = float(n) * n
+
+    def gbs(bytes_per_pt, k):
+        return bytes_per_pt * pts * prof["tile_frames"] / (kms[k] * 1e-3) / 1e9 if kms[k] > 0 else None
+
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(args.workload, {}).get(names[dom])
+        except Exception:
+            traffic = None
+    achieved = gbs(BYTES_PER_POINT[names[dom]], dom)
+    roofline = {
+        "bound": "hbm", "kernel": {"K1": "wso_pass1_kernel (evolve + first transform)",
+                                   "K2": "wso_pass2_kernel (second transform + pack)",
+                                   "K3": "wso_normalize_kernel"}[names[dom]],
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
+        "peak_source": peak_src, "traffic": traffic,
+        "algorithmic_bytes_per_launch": BYTES_PER_POINT[names[dom]] * pts * prof["tile_frames"] / max(prof["launches"], 1),
+        "avg_launch_ms": kms[dom] / max(prof["launches"], 1),
+        "timing": "cudaEvent pairs around every launch on the compute stream, separate pass over the same K steps",
+        "kernel_ms": dict(zip(names, kms)),
+        "kernel_share": dict(zip(names, [x / sum(kms) for x in kms])),
+        "per_kernel_achieved_gbs": {nm: gbs(BYTES_PER_POINT[nm], i) for i, nm in enumerate(names)},
+        "survey_model_achieved_gbs": gbs(SURVEY_BYTES_PER_POINT[names[dom]], dom),
+        "whole_path_gbs": sum(BYTES_PER_POINT.values()) * pts * world * F * args.steps / (ms * 1e-3) / 1e9,
+    }
+
+    # ---- end to end: host output buffers, D2H inside the timed region ---------------------------------
+    Fe = args.e2e_frames or min(F, 24)
+    disp = W.PinnedBuffer((Fe, n, n, 4))
+    norm = W.PinnedBuffer((Fe, n, n, 4))
+
+    def e2e_step(k):
+        t, tl = step_times(wl, k)
+        a, mn, mx = ws.compute_to_host(t[:Fe], disp.array, norm.array, tiles=None if tl is None else tl[:Fe])
+        return a
+
+    for k in range(args.warmup):
+        e2e_step(k)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.warmup, args.warmup + args.steps):
+        amps = e2e_step(k)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e_val = world * Fe * args.steps / e2e_s
+    all_amps = sharding.gather_in_global_order(amps.tolist(), Fe * world, rank, world) if world > 1 else amps
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            cpu = measure_cpu_baseline(wl)
+        except Exception as ex:  # the baseline is reported, never required
+            cpu = {"value": None, "unit": "tile-frames/s", "cores": 0, "kind": "unavailable", "sample": repr(ex)}
+
+    if rank == 0:
+        line = {
+            "metric": "ocean tile-frames/s", "value": value, "unit": "tile-frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": wl["desc"], "tile_size": n, "frames_per_step_per_gpu": F,
+                       "chunk_tile_frames_per_launch": ws.stats()["chunk"],
+                       "l2": f"outputs of one step = {F} slots x {32 * n * n / 1e6:.0f} MB > 126 MB L2; h0 is "
+                             "resident by design (same spectrum every frame)",
+                       "parallelism": f"frames sharded per GPU x{world}, no collective"},
+            "us_per_tile_frame": ms * 1e3 / (F * args.steps),
+            "e2e": {"value": e2e_val, "unit": "tile-frames/s", "h2d_bytes_per_step": int(4 * Fe),
+                    "d2h_bytes_per_step": int(2 * 16 * n * n * Fe + 12 * Fe), "frames_per_step_per_gpu": Fe,
+                    "api": "wso_compute_to_host (C ABI), pinned host maps, copies overlapped with the next chunk",
+                    "last_amplitude": float(all_amps[-1])},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    disp.close()
+    norm.close()
+    ws.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,91 @@
+// TEST INFRASTRUCTURE — CPU emulation of the CUDA kernel bodies.
+//
+// Compiles watersurfacerendering_b200/csrc/wso_kernels.cuh with g++ and steps every CTA thread by thread
+// (HostExec) so that the index / Hermitian-layout logic of the sm_100a kernels can be checked against the
+// oracle in the GPU-less build container.  Never linked into the product library; tests only.
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "wso_kernels.cuh"
+
+using namespace wso;
+
+template <int LOGN, int CP, int NF, int RI>
+static int run_cfg(const float* amp_t, const float* omega_t, const float* kv, float lambda, float t,
+                   float* disp, float* norm, float* minmax, float* amp_out, float* w_out) {
+    constexpr int N = 1 << LOGN, H = N / 2;
+    using P1 = Pass1<LOGN, CP, NF>;
+    using P2 = Pass2<LOGN, RI>;
+    std::vector<float2> tw(N);
+    for (int k = 0; k < N; ++k) {
+        const double a = 2.0 * 3.14159265358979323846 * k / N;
+        tw[k] = make_float2((float)cos(a), (float)sin(a));
+    }
+    TileDev td;
+    td.amp = reinterpret_cast<const float2*>(amp_t);
+    td.omega = omega_t;
+    td.kv = kv;
+    td.lambda = lambda;
+    td.pad_ = 0;
+    std::vector<float2> W((size_t)H * 4 * N);
+    LaunchArgs args;
+    std::memset(&args, 0, sizeof(args));
+    args.tiles = &td;
+    args.tw = tw.data();
+    args.W = W.data();
+    args.disp = reinterpret_cast<float4*>(disp);
+    args.norm = reinterpret_cast<float4*>(norm);
+    args.minmax = minmax;
+    args.amp_out = amp_out;
+    args.items[0].tile = 0;
+    args.items[0].slot = 0;
+    args.items[0].t = t;
+    {
+        std::vector<float2> smem(P1::SMEM_BYTES / sizeof(float2));
+        std::vector<ThreadState> st(P1::T);
+        for (int by = 0; by < 4 / NF; ++by)
+            for (int bx = 0; bx < H / CP; ++bx) {
+                for (auto& v : smem) v = make_float2(NAN, NAN);
+                HostExec ex{P1::T, st.data()};
+                P1::run(ex, smem.data(), bx, by, 0, args);
+            }
+    }
+    if (w_out) std::memcpy(w_out, W.data(), W.size() * sizeof(float2));
+    {
+        std::vector<float2> smem(P2::SMEM_BYTES / sizeof(float2));
+        std::vector<ThreadState> st(P2::T);
+        for (int by = 0; by < 2; ++by)
+            for (int bx = 0; bx < H / RI; ++bx) {
+                for (auto& v : smem) v = make_float2(NAN, NAN);
+                HostExec ex{P2::T, st.data()};
+                P2::run(ex, smem.data(), bx, by, 0, args);
+            }
+    }
+    const float a = amplitude_of(minmax[0], minmax[1]);
+    const float inv = 1.0f / a;
+    for (size_t i = 0; i < (size_t)N * N; ++i) disp[4 * i + 1] *= inv;
+    *amp_out = a;
+    return 0;
+}
+
+extern "C" int wso_emu_compute(int logn, int variant, const float* amp_t, const float* omega_t,
+                               const float* kv, float lambda, float t, float* disp, float* norm,
+                               float* minmax, float* amp_out, float* w_out) {
+#define CFG(L, V, CP, NF, RI) \
+    if (logn == L && variant == V) return run_cfg<L, CP, NF, RI>(amp_t, omega_t, kv, lambda, t, disp, norm, minmax, amp_out, w_out);
+    CFG(4, 0, 8, 4, 8)
+    CFG(4, 1, 2, 1, 1)
+    CFG(5, 0, 8, 4, 8)
+    CFG(6, 0, 8, 4, 8)
+    CFG(6, 1, 4, 2, 2)
+    CFG(6, 2, 1, 1, 1)
+    CFG(7, 0, 4, 4, 8)
+    CFG(8, 0, 4, 4, 4)
+    CFG(8, 1, 4, 2, 2)
+    CFG(9, 0, 4, 4, 4)
+    CFG(9, 1, 4, 2, 2)
+    CFG(10, 0, 4, 2, 4)
+#undef CFG
+    return -1;
+}

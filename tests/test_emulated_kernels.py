@@ -1,0 +1,79 @@
+"""CPU emulation of the sm_100a kernel bodies (tests/emu) versus the reference fixtures and the oracle.
+
+The exact code of wso_kernels.cuh / wso_device.cuh (evolve + Hermitian packing, Stockham stages, shared-memory
+layout, split/pack index logic) is compiled by g++ and stepped thread by thread.  This checks layout and index
+logic without a GPU; the GPU parity tests (-m gpu) check the real thing.
+"""
+import numpy as np
+import pytest
+
+import packed_model as M
+from conftest import SCALAR_REL_TOL, assert_maps_close, h0_struct, load_golden, rel_l2
+from emu import driver as E
+from oracle import port as P
+
+
+@pytest.mark.parametrize("name,variants", [("n16_default", (0, 1)), ("n64_default", (0, 1, 2)),
+                                           ("n64_wind", (0, 1)), ("n256_default", (0, 1))])
+def test_emulated_kernels_vs_reference_fixture(name, variants):
+    g, params = load_golden(name)
+    h0 = g["h0"]
+    for v in variants:
+        for i, t in enumerate(g["t"]):
+            a, disp, norm, mn, mx, _ = E.compute(params["tile_size"], params["tile_length"], params["lam"],
+                                                 h0[..., 0], h0[..., 1], h0[..., 4], float(t), variant=v)
+            assert_maps_close(disp, norm, g["disp"][i], g["norm"][i], f"{name} v{v} t={t}")
+            assert abs(a - g["A"][i]) <= SCALAR_REL_TOL * g["A"][i]
+            assert abs(mn - g["minh"][i]) <= SCALAR_REL_TOL * g["A"][i]
+            assert abs(mx - g["maxh"][i]) <= SCALAR_REL_TOL * g["A"][i]
+
+
+def test_emulated_intermediate_layout_matches_model():
+    """K1's Hermitian-packed intermediate W[m'][f][slot] bin-for-bin against the float64 model."""
+    g, params = load_golden("n64_wind")
+    h0 = g["h0"]
+    n = params["tile_size"]
+    t = float(g["t"][1])
+    _, _, _, _, _, w = E.compute(n, params["tile_length"], params["lam"], h0[..., 0], h0[..., 1], h0[..., 4],
+                                 t, variant=1, want_w=True)
+    idx = np.arange(n, dtype=np.float32)
+    kv = (np.pi * (np.float32(2) * idx - np.float32(n)).astype(np.float64)
+          / np.float64(np.float32(params["tile_length"]))).astype(np.float32)
+    Wm = M.pass1(M.evolve_Z(n, kv, h0[..., 0], h0[..., 1], h0[..., 4], t))
+    for f in range(4):
+        assert rel_l2(w[:, f, :], Wm[:, f, :]) < 2e-6, f"field {f}"
+
+
+@pytest.mark.parametrize("n,variant", [(512, 1), (1024, 0)])
+def test_emulated_kernels_vs_oracle_large(n, variant):
+    rng = np.random.default_rng(n)
+    xi = (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))).astype(np.complex64)
+    p = P.OceanParams(tile_size=n, tile_length=1000.0 * n / 512)
+    o = P.PortOracle(p)
+    h0 = o.prepare(xi)
+    t = 37.125
+    a_ref, d_ref, n_ref = o.compute_waves(t)
+    a, disp, norm, mn, mx, _ = E.compute(n, p.tile_length, p.lam, h0["re"], h0["im"], h0["omega"], t,
+                                         variant=variant)
+    assert_maps_close(disp, norm, d_ref, n_ref, f"N={n}")
+    assert abs(a - a_ref) <= SCALAR_REL_TOL * a_ref
+
+
+def test_one_hot_layout():
+    """One-hot h0 at special wave vectors (index 0 = Nyquist line, N/2 = DC line, N-1) must light up
+    exactly the oracle's pattern (index / Hermitian layout check)."""
+    n = 16
+    p = P.OceanParams(tile_size=n, tile_length=40.0)
+    o = P.PortOracle(p)
+    for (m, c) in [(0, 0), (0, 5), (5, 0), (n // 2, 3), (3, n // 2), (n - 1, n - 1), (1, n - 1), (n // 2, n // 2),
+                   (7, 9), (0, n // 2)]:
+        h0 = np.zeros((n, n), P.H0_DTYPE)
+        h0[m, c] = (0.7, -0.3, 0.7, 0.3, 0.31415927)
+        o.import_h0(h0)
+        a_ref, d_ref, n_ref = o.compute_waves(3.0)
+        a, disp, norm, mn, mx, _ = E.compute(n, p.tile_length, p.lam, h0["re"], h0["im"], h0["omega"], 3.0)
+        if a_ref > 1e-30:
+            scale = max(np.abs(d_ref[..., :3]).max(), 1e-30)
+            assert np.abs(disp[..., :3] - d_ref[..., :3]).max() <= 2e-6 * scale, (m, c)
+            scale = max(np.abs(n_ref).max(), 1e-30)
+            assert np.abs(norm - n_ref).max() <= 2e-6 * scale, (m, c)

@@ -1,0 +1,280 @@
+"""GPU parity tests (-m gpu): the sm_100a path, called through the C ABI (ctypes -> libwsocean.so), against
+the oracle on the same h0.
+
+Gate (BASELINE.json north_star): per map channel rel-L2 <= 1e-5 and max-abs <= 1e-4 x channel range in
+fp32; amplitude/min/max rel <= 1e-6; disp.w == 1.0 exactly; index/Hermitian layout exact
+(one-hot tests).  /root/reference is never read here: the oracle is oracle/libwsoracle.so (restatement,
+pinned in tests/test_oracle.py) and the committed fixtures under tests/golden/.
+"""
+import numpy as np
+import pytest
+
+from conftest import SCALAR_REL_TOL, assert_maps_close, h0_struct, load_golden, rel_l2
+from oracle import port as P
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def wso():
+    import watersurfacerendering_b200 as W
+    return W
+
+
+def _oracle_for(n, L=None, seed=0, **kw):
+    L = 1000.0 * n / 512 if L is None else L
+    p = P.OceanParams(tile_size=n, tile_length=L, **kw)
+    o = P.PortOracle(p)
+    rng = np.random.default_rng(seed + n)
+    xi = (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))).astype(np.complex64)
+    o.prepare(xi)
+    return p, o, xi
+
+
+def _apply_params(ws, p: P.OceanParams, tile=0):
+    ws.SetTileLength(p.tile_length, tile)
+    ws.SetWindDirection((p.wind_x, p.wind_y), tile)
+    ws.SetWindSpeed(p.wind_speed, tile)
+    ws.SetPhillipsConst(p.phillips_const, tile)
+    ws.SetDamping(p.damping, tile)
+    ws.SetAnimationPeriod(p.anim_period, tile)
+    ws.SetLambda(p.lam, tile)
+
+
+def _check_frame(ws, o, t, what):
+    a = ws.ComputeWaves(t)
+    a_ref, d_ref, n_ref = o.compute_waves(t)
+    assert_maps_close(ws.GetDisplacements(), ws.GetNormals(), d_ref, n_ref, what)
+    assert abs(a - a_ref) <= SCALAR_REL_TOL * a_ref, (what, a, a_ref)
+    assert abs(ws.GetMinHeight() - o.min_height) <= SCALAR_REL_TOL * a_ref
+    assert abs(ws.GetMaxHeight() - o.max_height) <= SCALAR_REL_TOL * a_ref
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["n16_default", "n64_default", "n64_wind", "n256_default"])
+def test_reference_fixtures(wso, name):
+    """Outputs of the reference's own code (tests/golden) for the exported h0."""
+    g, params = load_golden(name)
+    with wso.WSTessendorf(params["tile_size"], params["tile_length"]) as ws:
+        ws.SetLambda(params["lam"])
+        ws.ImportH0(h0_struct(g["h0"]))
+        for i, t in enumerate(g["t"]):
+            a = ws.ComputeWaves(float(t))
+            assert_maps_close(ws.GetDisplacements(), ws.GetNormals(), g["disp"][i], g["norm"][i], f"{name} t={t}")
+            assert abs(a - g["A"][i]) <= SCALAR_REL_TOL * g["A"][i]
+            assert abs(ws.GetMinHeight() - g["minh"][i]) <= SCALAR_REL_TOL * g["A"][i]
+            assert abs(ws.GetMaxHeight() - g["maxh"][i]) <= SCALAR_REL_TOL * g["A"][i]
+
+
+@pytest.mark.parametrize("name", ["n16_default", "n64_default", "n64_wind", "n256_default"])
+def test_prepare_reproduces_reference_h0_bit_exact(wso, name):
+    """Prepare() with srand(seed): same rand() consumption, same fp32 Phillips arithmetic as the reference."""
+    g, params = load_golden(name)
+    with wso.WSTessendorf(params["tile_size"], params["tile_length"]) as ws:
+        _apply_params(ws, P.OceanParams(**params))
+        ws.Prepare(seed=int(g["seed"]))
+        assert ws.ExportH0().tobytes() == h0_struct(g["h0"]).tobytes()
+        ws.PrepareWithGauss(g["xi"])
+        assert ws.ExportH0().tobytes() == h0_struct(g["h0"]).tobytes()
+
+
+@pytest.mark.parametrize("n", [16, 32, 64, 128, 256, 512, 1024, 2048])
+def test_all_tile_sizes_vs_oracle(wso, n):
+    p, o, xi = _oracle_for(n)
+    times = [0.0, 1.5, 4711.25] if n <= 1024 else [36.6]
+    with wso.WSTessendorf(n, p.tile_length) as ws:
+        ws.PrepareWithGauss(xi)
+        assert ws.ExportH0().tobytes() == o.h0.tobytes()
+        for t in times:
+            _check_frame(ws, o, t, f"N={n} t={t}")
+
+
+def test_4096_vs_oracle(wso):
+    n = 4096
+    p, o, xi = _oracle_for(n)
+    with wso.WSTessendorf(n, p.tile_length) as ws:
+        ws.PrepareWithGauss(xi)
+        _check_frame(ws, o, 12.5, "N=4096")
+
+
+@pytest.mark.parametrize("kw", [
+    dict(wind_x=-0.3, wind_y=1.0, wind_speed=8.0, lam=-0.5),
+    dict(wind_x=1.0, wind_y=0.0, wind_speed=55.0, damping=0.4, lam=1.25),
+    dict(phillips_const=9e-7, anim_period=60.0, lam=0.0),
+    dict(wind_speed=1e-9),   # clamped to 1e-4 like SetWindSpeed: an (almost) flat ocean
+])
+def test_parameter_variants(wso, kw):
+    n = 128
+    p, o, xi = _oracle_for(n, L=77.0, seed=5, **kw)
+    with wso.WSTessendorf(n, 77.0) as ws:
+        _apply_params(ws, p)
+        ws.PrepareWithGauss(xi)
+        assert ws.ExportH0().tobytes() == o.h0.tobytes()
+        a_ref, d_ref, n_ref = o.compute_waves(9.75)
+        if not np.isfinite(a_ref) or a_ref < 1e-30:
+            pytest.skip("degenerate ocean (reference divides by A = 0)")
+        _check_frame(ws, o, 9.75, str(kw))
+
+
+def test_lambda_takes_effect_without_prepare(wso):
+    """reference: SetLambda needs no Prepare() (WaterSurfaceMesh.cpp:902)."""
+    n = 64
+    p, o, xi = _oracle_for(n)
+    with wso.WSTessendorf(n, p.tile_length) as ws:
+        ws.PrepareWithGauss(xi)
+        for lam in (-1.0, 0.35, 2.0):
+            ws.SetLambda(lam)
+            o.p.lam = lam
+            assert ws.GetDisplacementLambda() == np.float32(lam)
+            _check_frame(ws, o, 3.25, f"lambda={lam}")
+
+
+def test_one_hot_layout(wso):
+    """Index / Hermitian layout: a single non-zero wave vector at the special indices (0 = Nyquist line,
+    N/2 = DC line, N-1, and generic) must produce exactly the oracle's pattern."""
+    n = 32
+    p = P.OceanParams(tile_size=n, tile_length=40.0)
+    o = P.PortOracle(p)
+    with wso.WSTessendorf(n, 40.0) as ws:
+        for (m, c) in [(0, 0), (0, 5), (5, 0), (n // 2, 3), (3, n // 2), (n - 1, n - 1), (1, n - 1),
+                       (7, 9), (0, n // 2), (n // 2, 0), (n - 1, 0), (17, 30)]:
+            h0 = np.zeros((n, n), P.H0_DTYPE)
+            h0[m, c] = (0.7, -0.3, 0.7, 0.3, 0.31415927)
+            o.import_h0(h0)
+            ws.ImportH0(h0)
+            a_ref, d_ref, n_ref = o.compute_waves(3.0)
+            a = ws.ComputeWaves(3.0)
+            assert abs(a - a_ref) <= 2e-6 * a_ref
+            d, nm = ws.GetDisplacements(), ws.GetNormals()
+            assert np.abs(d[..., :3] - d_ref[..., :3]).max() <= 2e-6 * np.abs(d_ref[..., :3]).max(), (m, c)
+            assert np.abs(nm - n_ref).max() <= 2e-6 * max(np.abs(n_ref).max(), 1e-30), (m, c)
+            assert np.all(d[..., 3] == 1.0)
+
+
+def test_batch_matches_single_frames(wso):
+    """Animation frames are independent (BASELINE config 2/3): a batch == the same frames one by one."""
+    n = 256
+    p, o, xi = _oracle_for(n)
+    times = np.array([0.05 * i for i in range(37)], np.float32)   # 37: not a multiple of the chunk
+    with wso.WSTessendorf(n, p.tile_length, max_slots=40) as ws:
+        ws.PrepareWithGauss(xi)
+        ws.compute_batch(times, first_slot=2)
+        a, mn, mx = ws.read_heights(2, times.size)
+        for i in (0, 1, 17, 36):
+            d = ws.copy_map(0, 2 + i)
+            nm = ws.copy_map(1, 2 + i)
+            a1 = ws.ComputeWaves(float(times[i]))
+            assert a1 == a[i] and ws.GetMinHeight() == mn[i] and ws.GetMaxHeight() == mx[i]
+            assert d.tobytes() == ws.GetDisplacements().tobytes()
+            assert nm.tobytes() == ws.GetNormals().tobytes()
+        a_ref, d_ref, n_ref = o.compute_waves(float(times[36]))
+        assert_maps_close(ws.copy_map(0, 38), ws.copy_map(1, 38), d_ref, n_ref, "batch frame 36")
+
+
+def test_independent_tiles_in_one_batch(wso):
+    """BASELINE config 4 in miniature: tiles with different wind / seed, batched in one launch."""
+    n, ntiles = 128, 5
+    oracles = []
+    with wso.WSTessendorf(n, 250.0, max_tiles=ntiles, max_slots=ntiles) as ws:
+        for j in range(ntiles):
+            ang = 2 * np.pi * j / ntiles
+            p, o, xi = _oracle_for(n, L=250.0, seed=1000 + j, wind_x=float(np.cos(ang)),
+                                   wind_y=float(np.sin(ang)), wind_speed=5.0 + 4.0 * j, lam=-1.0 + 0.3 * j)
+            _apply_params(ws, p, tile=j)
+            ws.PrepareWithGauss(xi, tile=j)
+            assert ws.ExportH0(tile=j).tobytes() == o.h0.tobytes()
+            oracles.append(o)
+        ws.compute_batch(np.full(ntiles, 10.0, np.float32), tiles=np.arange(ntiles))
+        a, mn, mx = ws.read_heights(0, ntiles)
+        for j, o in enumerate(oracles):
+            a_ref, d_ref, n_ref = o.compute_waves(10.0)
+            assert_maps_close(ws.copy_map(0, j), ws.copy_map(1, j), d_ref, n_ref, f"tile {j}")
+            assert abs(a[j] - a_ref) <= SCALAR_REL_TOL * a_ref
+
+
+def test_compute_to_host_streams_every_frame(wso):
+    n = 256
+    p, o, xi = _oracle_for(n)
+    with wso.WSTessendorf(n, p.tile_length, max_slots=128) as ws:
+        ws.PrepareWithGauss(xi)
+        chunk = ws.stats()["chunk"]
+        nfr = 2 * chunk + 3 if chunk < 40 else chunk + 3
+        times = np.linspace(0.0, 50.0, nfr).astype(np.float32)
+        disp = wso.PinnedBuffer((nfr, n, n, 4))
+        norm = wso.PinnedBuffer((nfr, n, n, 4))
+        a, mn, mx = ws.compute_to_host(times, disp.array, norm.array)
+        for i in (0, chunk - 1, min(chunk, nfr - 1), nfr - 1):
+            a1 = ws.ComputeWaves(float(times[i]))
+            assert a1 == a[i]
+            assert disp.array[i].tobytes() == ws.GetDisplacements().tobytes()
+            assert norm.array[i].tobytes() == ws.GetNormals().tobytes()
+        a_ref, d_ref, n_ref = o.compute_waves(float(times[-1]))
+        assert_maps_close(disp.array[-1], norm.array[-1], d_ref, n_ref, "streamed last frame")
+        disp.close()
+        norm.close()
+
+
+def test_tile_size_change_and_ignored_sizes(wso):
+    """reference: SetTileSize ignores non-powers-of-two (WSTessendorf.cpp:459-468); a new size applies at Prepare."""
+    with wso.WSTessendorf(64, 100.0) as ws:
+        assert ws.SetTileSize(100) is False and ws.GetTileSize() == 64
+        assert ws.SetTileSize(128) is True
+        p, o, xi = _oracle_for(128, L=100.0)
+        ws.PrepareWithGauss(xi)
+        _check_frame(ws, o, 2.0, "resized to 128")
+
+
+def test_error_codes(wso):
+    from watersurfacerendering_b200 import _lib as L
+    with wso.WSTessendorf(32, 50.0) as ws:
+        with pytest.raises(L.WsoError) as e:
+            ws.ComputeWaves(0.0)
+        assert e.value.status == L.WSO_ERR_NOT_PREPARED
+        h0 = np.zeros((32, 32), P.H0_DTYPE)
+        h0[3, 4] = (0.5, 0.25, 0.5, 0.25, 1.0)   # conj amplitude is NOT the conjugate
+        with pytest.raises(L.WsoError) as e:
+            ws.ImportH0(h0)
+        assert e.value.status == L.WSO_ERR_H0_NOT_CONJUGATE
+        with pytest.raises(L.WsoError) as e:
+            ws.compute_batch([0.0, 1.0])          # only one slot
+        assert e.value.status in (L.WSO_ERR_INVALID_ARG, L.WSO_ERR_NOT_PREPARED)
+
+
+def test_full_size_properties_2048(wso):
+    """Size-independent properties at a BASELINE size: point symmetry, Parseval on the
+    height field, disp.w == 1, |disp.y| <= 1 with the bound attained, and 24 texels against the direct
+    float64 Fourier sum."""
+    n = 2048
+    p, o, xi = _oracle_for(n, seed=2)
+    t = 0.05 * 41
+    with wso.WSTessendorf(n, p.tile_length) as ws:
+        ws.PrepareWithGauss(xi)
+        a = float(ws.ComputeWaves(t))
+        d = ws.GetDisplacements().copy()
+        nm = ws.GetNormals().copy()
+    h0 = o.h0
+    ph = (h0["omega"] * np.float32(t)).astype(np.float32).astype(np.float64)
+    H = 2.0 * (h0["re"].astype(np.float64) * np.cos(ph) - h0["im"].astype(np.float64) * np.sin(ph))
+
+    def refl(x):
+        return np.roll(x[::-1, ::-1], (1, 1), axis=(0, 1))
+
+    assert np.all(d[..., 3] == 1.0)
+    assert abs(np.abs(d[..., 1]).max() - 1.0) < 1e-6
+    height = d[..., 1].astype(np.float64) * a
+    assert np.abs(height - refl(height)).max() < 2e-5 * a
+    for ch in (d[..., 0], d[..., 2], nm[..., 0], nm[..., 1]):
+        ch = ch.astype(np.float64)
+        assert np.abs(ch + refl(ch)).max() < 2e-5 * np.abs(ch).max()
+    # Parseval: sum_x h^2 = N^2 sum_k |Y|^2 with Y the Hermitian part of the (real) spectrum
+    Y = 0.5 * (H + refl(H))
+    assert abs(np.sum(height ** 2) / (n * n * np.sum(Y ** 2)) - 1.0) < 1e-5
+    # direct Fourier sum at random texels
+    rng = np.random.default_rng(0)
+    mm = np.arange(n)
+    for _ in range(24):
+        r, c = int(rng.integers(n)), int(rng.integers(n))
+        er = np.exp(2j * np.pi * (mm * r % n) / n)
+        ec = np.exp(2j * np.pi * (mm * c % n) / n)
+        val = np.real(er @ H @ ec) * (-1.0 if (r + c) & 1 else 1.0)
+        assert abs(height[r, c] - val) < 2e-5 * a, (r, c)

@@ -1,0 +1,640 @@
+// wso_api.cu — the C ABI (include/wsocean.h): context, buffers, Prepare(), batching, host copies.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "wso_host_prepare.h"
+#include "wso_kernels.cuh"
+#include "wso_launch.h"
+#include "wsocean.h"
+
+using wso::BatchItem;
+using wso::LaunchArgs;
+using wso::TileDev;
+
+namespace {
+
+std::mutex g_err_mutex;
+std::string g_create_error;
+
+struct Tile {
+    wso_params params;          // as set (pending until the next prepare, except lambda)
+    wso_params prepared;        // parameters the resident h0 was built with
+    bool is_prepared = false;
+    std::vector<wso_h0_record> h0;  // host copy in the reference layout (export / checkpoint)
+};
+
+}  // namespace
+
+struct wso_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaStream_t stream = nullptr;  // the one kernels run on (own_stream unless wso_set_stream)
+    cudaEvent_t ev_chunk[2] = {nullptr, nullptr};
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr};
+    uint32_t n = 0;
+    int logn = 0;
+    uint32_t max_tiles = 1, max_slots = 1;
+    uint32_t chunk = 1;
+    bool first_use = true;
+    uint64_t launches = 0;
+    std::vector<Tile> tiles;
+    // device
+    float2* d_amp = nullptr;     // [tile][n][m]
+    float* d_omega = nullptr;    // [tile][n][m]
+    float* d_kv = nullptr;       // [tile][N]
+    TileDev* d_tiles = nullptr;  // [tile]
+    float2* d_tw = nullptr;      // [N]
+    float2* d_W = nullptr;       // [2][chunk][N/2][4][N]  (double buffered across chunks)
+    float4* d_disp = nullptr;    // [slot][N*N]
+    float4* d_norm = nullptr;
+    float* d_minmax = nullptr;   // [slot][2]
+    float* d_ampl = nullptr;     // [slot]
+    // pinned host
+    float4* h_disp = nullptr;    // slot 0 mirror for wso_compute / wso_map_host
+    float4* h_norm = nullptr;
+    float* h_small = nullptr;    // [small_cap][3] amplitude,min,max staging
+    size_t small_cap = 0;
+    std::vector<TileDev> h_tiles;
+    // opt-in per-kernel timing (wso_set_profiling): one event quad per chunk launch, resolved lazily
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events;  // 4 per launch
+    size_t prof_used = 0;                  // events handed out since the last resolve
+    double prof_ms[3] = {0.0, 0.0, 0.0};
+    uint64_t prof_launches = 0;
+    uint64_t prof_items = 0;
+    std::string err;
+};
+
+namespace {
+
+int fail(wso_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg;
+    else {
+        std::lock_guard<std::mutex> lk(g_err_mutex);
+        g_create_error = msg;
+    }
+    return code;
+}
+int fail_cuda(wso_ctx* c, cudaError_t e, const char* what) {
+    const int code = (e == cudaErrorMemoryAllocation) ? WSO_ERR_OUT_OF_MEMORY : WSO_ERR_CUDA;
+    return fail(c, code, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define WSO_CUDA(c, call)                                   \
+    do {                                                    \
+        cudaError_t e_ = (call);                            \
+        if (e_ != cudaSuccess) return fail_cuda(c, e_, #call); \
+    } while (0)
+
+bool valid_tile_size(uint32_t n, int* logn) {
+    if (n == 0 || (n & (n - 1)) != 0) return false;
+    int l = 0;
+    while ((1u << l) < n) ++l;
+    if (l < wso::kMinLogN || l > wso::kMaxLogN) return false;
+    if (logn) *logn = l;
+    return true;
+}
+
+bool valid_params(const wso_params& p) {
+    if (!(p.tile_length > 0.0f)) return false;
+    if (!(p.wind_dir_x != 0.0f || p.wind_dir_y != 0.0f)) return false;
+    if (!std::isfinite(p.wind_dir_x) || !std::isfinite(p.wind_dir_y)) return false;
+    if (!(p.anim_period > 0.0f)) return false;
+    if (!std::isfinite(p.wind_speed) || !std::isfinite(p.phillips_const) || !std::isfinite(p.damping) ||
+        !std::isfinite(p.lambda))
+        return false;
+    return true;
+}
+
+void free_device_buffers(wso_ctx* c) {
+    cudaFree(c->d_amp); c->d_amp = nullptr;
+    cudaFree(c->d_omega); c->d_omega = nullptr;
+    cudaFree(c->d_kv); c->d_kv = nullptr;
+    cudaFree(c->d_tiles); c->d_tiles = nullptr;
+    cudaFree(c->d_tw); c->d_tw = nullptr;
+    cudaFree(c->d_W); c->d_W = nullptr;
+    cudaFree(c->d_disp); c->d_disp = nullptr;
+    cudaFree(c->d_norm); c->d_norm = nullptr;
+    cudaFree(c->d_minmax); c->d_minmax = nullptr;
+    cudaFree(c->d_ampl); c->d_ampl = nullptr;
+    cudaFreeHost(c->h_disp); c->h_disp = nullptr;
+    cudaFreeHost(c->h_norm); c->h_norm = nullptr;
+    cudaFreeHost(c->h_small); c->h_small = nullptr;
+}
+
+// (Re)allocate everything that depends on the tile size.
+int allocate_for_size(wso_ctx* c, uint32_t n) {
+    int logn = 0;
+    if (!valid_tile_size(n, &logn)) return fail(c, WSO_ERR_BAD_TILE_SIZE, "tile size must be a power of two in [16, 8192]");
+    WSO_CUDA(c, cudaSetDevice(c->device));
+    WSO_CUDA(c, cudaStreamSynchronize(c->stream));
+    free_device_buffers(c);
+    c->n = n;
+    c->logn = logn;
+    c->first_use = true;
+    const size_t n2 = (size_t)n * n;
+    // chunk: tile-frames per launch.  Keep the W scratch of one chunk around 48 MB so it stays in the
+    // 126 MB L2 between K1 and K2.
+    const size_t w_item = n2 * 16;
+    size_t chunk = (48u << 20) / w_item;
+    if (chunk < 1) chunk = 1;
+    if (chunk > (size_t)wso::kMaxChunk) chunk = wso::kMaxChunk;
+    if (chunk > c->max_slots) chunk = c->max_slots;
+    c->chunk = (uint32_t)chunk;
+    WSO_CUDA(c, cudaMalloc(&c->d_amp, sizeof(float2) * n2 * c->max_tiles));
+    WSO_CUDA(c, cudaMalloc(&c->d_omega, sizeof(float) * n2 * c->max_tiles));
+    WSO_CUDA(c, cudaMalloc(&c->d_kv, sizeof(float) * n * c->max_tiles));
+    WSO_CUDA(c, cudaMalloc(&c->d_tiles, sizeof(TileDev) * c->max_tiles));
+    WSO_CUDA(c, cudaMalloc(&c->d_tw, sizeof(float2) * n));
+    WSO_CUDA(c, cudaMalloc(&c->d_W, w_item * chunk * 2));
+    WSO_CUDA(c, cudaMalloc(&c->d_disp, sizeof(float4) * n2 * c->max_slots));
+    WSO_CUDA(c, cudaMalloc(&c->d_norm, sizeof(float4) * n2 * c->max_slots));
+    WSO_CUDA(c, cudaMalloc(&c->d_minmax, sizeof(float) * 2 * c->max_slots));
+    WSO_CUDA(c, cudaMalloc(&c->d_ampl, sizeof(float) * c->max_slots));
+    WSO_CUDA(c, cudaMallocHost(&c->h_disp, sizeof(float4) * n2));
+    WSO_CUDA(c, cudaMallocHost(&c->h_norm, sizeof(float4) * n2));
+    c->small_cap = c->max_slots;
+    WSO_CUDA(c, cudaMallocHost(&c->h_small, sizeof(float) * 3 * c->small_cap));
+    // initial map contents as the reference's resize() defaults (WSTessendorf.cpp:50-54)
+    WSO_CUDA(c, cudaMemsetAsync(c->d_disp, 0, sizeof(float4) * n2 * c->max_slots, c->stream));
+    WSO_CUDA(c, cudaMemsetAsync(c->d_norm, 0, sizeof(float4) * n2 * c->max_slots, c->stream));
+    // twiddles exp(+2 pi i k / N), computed in float64
+    std::vector<float2> tw(n);
+    for (uint32_t k = 0; k < n; ++k) {
+        const double a = 2.0 * 3.14159265358979323846 * (double)k / (double)n;
+        tw[k] = make_float2((float)std::cos(a), (float)std::sin(a));
+    }
+    WSO_CUDA(c, cudaMemcpyAsync(c->d_tw, tw.data(), sizeof(float2) * n, cudaMemcpyHostToDevice, c->stream));
+    c->h_tiles.assign(c->max_tiles, TileDev{});
+    for (uint32_t t = 0; t < c->max_tiles; ++t) {
+        c->h_tiles[t].amp = c->d_amp + n2 * t;
+        c->h_tiles[t].omega = c->d_omega + n2 * t;
+        c->h_tiles[t].kv = c->d_kv + (size_t)n * t;
+        c->h_tiles[t].lambda = c->tiles[t].params.lambda;
+        c->tiles[t].is_prepared = false;
+        c->tiles[t].h0.clear();
+    }
+    WSO_CUDA(c, cudaMemcpyAsync(c->d_tiles, c->h_tiles.data(), sizeof(TileDev) * c->max_tiles,
+                                cudaMemcpyHostToDevice, c->stream));
+    WSO_CUDA(c, cudaStreamSynchronize(c->stream));
+    return WSO_OK;
+}
+
+// Upload one tile's h0 (reference layout, row-major [m][n]) as the transposed compact arrays the kernels read.
+int upload_h0(wso_ctx* c, uint32_t tile, const wso_h0_record* h0) {
+    const uint32_t n = c->n;
+    const size_t n2 = (size_t)n * n;
+    for (size_t i = 0; i < n2; ++i) {
+        // every reference-built h0 has heightAmp_conj == conj(heightAmp) (WSTessendorf.cpp:132-135)
+        if (!(h0[i].amp_conj_re == h0[i].amp_re && h0[i].amp_conj_im == -h0[i].amp_im))
+            return fail(c, WSO_ERR_H0_NOT_CONJUGATE, "h0: heightAmp_conj != conj(heightAmp)");
+    }
+    std::vector<float2> amp_t(n2);
+    std::vector<float> om_t(n2);
+    for (uint32_t m = 0; m < n; ++m)
+        for (uint32_t k = 0; k < n; ++k) {
+            const wso_h0_record& r = h0[(size_t)m * n + k];
+            amp_t[(size_t)k * n + m] = make_float2(r.amp_re, r.amp_im);
+            om_t[(size_t)k * n + m] = r.dispersion;
+        }
+    std::vector<float> kv;
+    wso::host_wave_numbers(n, c->tiles[tile].params.tile_length, kv);
+    WSO_CUDA(c, cudaSetDevice(c->device));
+    WSO_CUDA(c, cudaStreamSynchronize(c->stream));
+    WSO_CUDA(c, cudaMemcpy(c->d_amp + n2 * tile, amp_t.data(), sizeof(float2) * n2, cudaMemcpyHostToDevice));
+    WSO_CUDA(c, cudaMemcpy(c->d_omega + n2 * tile, om_t.data(), sizeof(float) * n2, cudaMemcpyHostToDevice));
+    WSO_CUDA(c, cudaMemcpy(c->d_kv + (size_t)n * tile, kv.data(), sizeof(float) * n, cudaMemcpyHostToDevice));
+    Tile& tl = c->tiles[tile];
+    if (tl.h0.data() != h0) tl.h0.assign(h0, h0 + n2);
+    tl.prepared = tl.params;
+    tl.is_prepared = true;
+    return WSO_OK;
+}
+
+int push_lambdas(wso_ctx* c) {
+    bool dirty = false;
+    for (uint32_t t = 0; t < c->max_tiles; ++t)
+        if (c->h_tiles[t].lambda != c->tiles[t].params.lambda) {
+            c->h_tiles[t].lambda = c->tiles[t].params.lambda;
+            dirty = true;
+        }
+    if (dirty)
+        WSO_CUDA(c, cudaMemcpyAsync(c->d_tiles, c->h_tiles.data(), sizeof(TileDev) * c->max_tiles,
+                                    cudaMemcpyHostToDevice, c->stream));
+    return WSO_OK;
+}
+
+// Prepare step shared by wso_prepare / wso_prepare_gauss: apply pending params (possibly a new size).
+int begin_prepare(wso_ctx* c, uint32_t tile) {
+    if (!c) return WSO_ERR_INVALID_ARG;
+    if (tile >= c->max_tiles) return fail(c, WSO_ERR_INVALID_ARG, "tile index out of range");
+    const wso_params& p = c->tiles[tile].params;
+    if (p.tile_size != c->n) {
+        const int rc = allocate_for_size(c, p.tile_size);
+        if (rc != WSO_OK) return rc;
+    }
+    return WSO_OK;
+}
+
+int enqueue_chunk(wso_ctx* c, uint32_t n_items, const uint32_t* tiles, const float* t, uint32_t first_slot,
+                  int wbuf) {
+    LaunchArgs args;
+    args.tiles = c->d_tiles;
+    args.tw = c->d_tw;
+    args.W = c->d_W + (size_t)wbuf * c->chunk * ((size_t)c->n * c->n * 2);
+    args.disp = c->d_disp;
+    args.norm = c->d_norm;
+    args.minmax = c->d_minmax;
+    args.amp_out = c->d_ampl;
+    for (uint32_t i = 0; i < n_items; ++i) {
+        args.items[i].tile = tiles ? tiles[i] : 0u;
+        args.items[i].slot = first_slot + i;
+        args.items[i].t = t[i];
+    }
+    for (uint32_t i = n_items; i < (uint32_t)wso::kMaxChunk; ++i) args.items[i] = BatchItem{0u, 0u, 0.0f};
+    cudaEvent_t* ev = nullptr;
+    if (c->profiling) {
+        if (c->prof_used + 4 > c->prof_events.size()) {
+            for (int i = 0; i < 4; ++i) {
+                cudaEvent_t x;
+                cudaError_t ee = cudaEventCreate(&x);
+                if (ee != cudaSuccess) return fail_cuda(c, ee, "cudaEventCreate");
+                c->prof_events.push_back(x);
+            }
+        }
+        ev = c->prof_events.data() + c->prof_used;
+        c->prof_used += 4;
+        c->prof_launches += 1;
+        c->prof_items += n_items;
+    }
+    cudaError_t e = wso::launch_compute_waves(c->logn, args, (int)n_items, c->stream, c->first_use, ev);
+    if (e != cudaSuccess) return fail_cuda(c, e, "kernel launch");
+    c->first_use = false;
+    c->launches += (uint64_t)wso::kernels_per_launch();
+    return WSO_OK;
+}
+
+int check_batch(wso_ctx* c, uint32_t n, const uint32_t* tiles, const float* t, uint32_t first_slot) {
+    if (!c) return WSO_ERR_INVALID_ARG;
+    if (!t) return fail(c, WSO_ERR_INVALID_ARG, "t is NULL");
+    if ((uint64_t)first_slot + n > c->max_slots) return fail(c, WSO_ERR_INVALID_ARG, "slots out of range");
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t tl = tiles ? tiles[i] : 0u;
+        if (tl >= c->max_tiles) return fail(c, WSO_ERR_INVALID_ARG, "tile index out of range");
+        if (!c->tiles[tl].is_prepared) return fail(c, WSO_ERR_NOT_PREPARED, "Prepare() has not been called for this tile");
+    }
+    return WSO_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int wso_default_params(wso_params* p) {
+    if (!p) return WSO_ERR_INVALID_ARG;
+    p->tile_size = 512;       // reference: WSTessendorf.h:36-43
+    p->tile_length = 1000.0f;
+    p->wind_dir_x = 1.0f;
+    p->wind_dir_y = 1.0f;
+    p->wind_speed = 30.0f;
+    p->anim_period = 200.0f;
+    p->phillips_const = 3e-7f;
+    p->damping = 0.1f;
+    p->lambda = -1.0f;        // reference: WSTessendorf.h:181
+    return WSO_OK;
+}
+
+int wso_create(const wso_params* p, int device, uint32_t max_tiles, uint32_t max_slots, wso_ctx** out) {
+    if (!p || !out || max_tiles == 0 || max_slots == 0) return fail(nullptr, WSO_ERR_INVALID_ARG, "bad argument");
+    *out = nullptr;
+    if (!valid_tile_size(p->tile_size, nullptr))
+        return fail(nullptr, WSO_ERR_BAD_TILE_SIZE, "tile size must be a power of two in [16, 8192]");
+    if (!valid_params(*p)) return fail(nullptr, WSO_ERR_INVALID_ARG, "invalid parameters");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, WSO_ERR_CUDA, std::string("no usable CUDA device (no CPU fallback exists): ") +
+                                               (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    if (device < 0 || device >= ndev) return fail(nullptr, WSO_ERR_INVALID_ARG, "device ordinal out of range");
+    wso_ctx* c = new (std::nothrow) wso_ctx();
+    if (!c) return fail(nullptr, WSO_ERR_OUT_OF_MEMORY, "host allocation failed");
+    c->device = device;
+    c->max_tiles = max_tiles;
+    c->max_slots = max_slots;
+    c->tiles.resize(max_tiles);
+    wso_params p0 = *p;
+    wso::normalise_like_setters(p0, nullptr);
+    for (auto& tl : c->tiles) tl.params = p0;
+    int rc = WSO_OK;
+    do {
+        if ((e = cudaSetDevice(device)) != cudaSuccess) { rc = fail_cuda(nullptr, e, "cudaSetDevice"); break; }
+        if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess) { rc = fail_cuda(nullptr, e, "cudaStreamCreate"); break; }
+        if ((e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) { rc = fail_cuda(nullptr, e, "cudaStreamCreate"); break; }
+        for (int i = 0; i < 2; ++i) {
+            if ((e = cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming)) != cudaSuccess) break;
+            if ((e = cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming)) != cudaSuccess) break;
+        }
+        if (e != cudaSuccess) { rc = fail_cuda(nullptr, e, "cudaEventCreate"); break; }
+        c->stream = c->own_stream;
+        rc = allocate_for_size(c, p->tile_size);
+        if (rc != WSO_OK) fail(nullptr, rc, c->err);
+    } while (0);
+    if (rc != WSO_OK) {
+        wso_destroy(c);
+        return rc;
+    }
+    *out = c;
+    return WSO_OK;
+}
+
+int wso_destroy(wso_ctx* c) {
+    if (!c) return WSO_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    free_device_buffers(c);
+    for (int i = 0; i < 2; ++i) {
+        if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]);
+        if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
+    }
+    for (cudaEvent_t x : c->prof_events) cudaEventDestroy(x);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    delete c;
+    return WSO_OK;
+}
+
+int wso_set_params(wso_ctx* c, uint32_t tile, const wso_params* p) {
+    if (!c || !p) return WSO_ERR_INVALID_ARG;
+    if (tile >= c->max_tiles) return fail(c, WSO_ERR_INVALID_ARG, "tile index out of range");
+    if (!valid_tile_size(p->tile_size, nullptr))
+        return fail(c, WSO_ERR_BAD_TILE_SIZE, "tile size must be a power of two in [16, 8192]; unchanged");
+    if (p->tile_size != c->n && c->max_tiles != 1)
+        return fail(c, WSO_ERR_INVALID_ARG, "tile size can only change on a single-tile context");
+    if (!valid_params(*p)) return fail(c, WSO_ERR_INVALID_ARG, "invalid parameters");
+    wso_params np = *p;
+    wso::normalise_like_setters(np, &c->tiles[tile].params);
+    c->tiles[tile].params = np;
+    return WSO_OK;
+}
+
+int wso_get_params(const wso_ctx* c, uint32_t tile, wso_params* p) {
+    if (!c || !p || tile >= c->max_tiles) return WSO_ERR_INVALID_ARG;
+    *p = c->tiles[tile].params;  // wind direction normalised / speed clamped at set time, like the reference
+    return WSO_OK;
+}
+
+int wso_set_lambda(wso_ctx* c, uint32_t tile, float lambda) {
+    if (!c || tile >= c->max_tiles || !std::isfinite(lambda)) return WSO_ERR_INVALID_ARG;
+    c->tiles[tile].params.lambda = lambda;
+    return WSO_OK;
+}
+
+int wso_prepare(wso_ctx* c, uint32_t tile, int reseed, unsigned seed) {
+    int rc = begin_prepare(c, tile);
+    if (rc != WSO_OK) return rc;
+    if (reseed) std::srand(seed);
+    std::vector<float> xi;
+    wso::host_gauss_array_from_rand(c->n, xi);
+    return wso_prepare_gauss(c, tile, xi.data());
+}
+
+int wso_prepare_gauss(wso_ctx* c, uint32_t tile, const float* xi) {
+    int rc = begin_prepare(c, tile);
+    if (rc != WSO_OK) return rc;
+    if (!xi) return fail(c, WSO_ERR_INVALID_ARG, "xi is NULL");
+    Tile& tl = c->tiles[tile];
+    wso::host_base_wave_heights(tl.params, xi, tl.h0);
+    return upload_h0(c, tile, tl.h0.data());
+}
+
+int wso_import_h0(wso_ctx* c, uint32_t tile, const wso_h0_record* h0) {
+    int rc = begin_prepare(c, tile);
+    if (rc != WSO_OK) return rc;
+    if (!h0) return fail(c, WSO_ERR_INVALID_ARG, "h0 is NULL");
+    return upload_h0(c, tile, h0);
+}
+
+int wso_export_h0(const wso_ctx* c, uint32_t tile, wso_h0_record* h0) {
+    if (!c || !h0 || tile >= c->max_tiles) return WSO_ERR_INVALID_ARG;
+    if (!c->tiles[tile].is_prepared) return WSO_ERR_NOT_PREPARED;
+    std::memcpy(h0, c->tiles[tile].h0.data(), sizeof(wso_h0_record) * c->tiles[tile].h0.size());
+    return WSO_OK;
+}
+
+int wso_compute_batch(wso_ctx* c, uint32_t n, const uint32_t* tiles, const float* t, uint32_t first_slot) {
+    int rc = check_batch(c, n, tiles, t, first_slot);
+    if (rc != WSO_OK) return rc;
+    WSO_CUDA(c, cudaSetDevice(c->device));
+    if ((rc = push_lambdas(c)) != WSO_OK) return rc;
+    int wbuf = 0;
+    for (uint32_t done = 0; done < n; done += c->chunk) {
+        const uint32_t m = (n - done < c->chunk) ? (n - done) : c->chunk;
+        rc = enqueue_chunk(c, m, tiles ? tiles + done : nullptr, t + done, first_slot + done, wbuf);
+        if (rc != WSO_OK) return rc;
+        wbuf ^= 1;
+    }
+    return WSO_OK;
+}
+
+int wso_sync(wso_ctx* c) {
+    if (!c) return WSO_ERR_INVALID_ARG;
+    WSO_CUDA(c, cudaSetDevice(c->device));
+    WSO_CUDA(c, cudaStreamSynchronize(c->stream));
+    WSO_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+    return WSO_OK;
+}
+
+int wso_read_heights(wso_ctx* c, uint32_t first_slot, uint32_t n, float* amplitude, float* min_height,
+                     float* max_height) {
+    if (!c) return WSO_ERR_INVALID_ARG;
+    if ((uint64_t)first_slot + n > c->max_slots) return fail(c, WSO_ERR_INVALID_ARG, "slots out of range");
+    WSO_CUDA(c, cudaSetDevice(c->device));
+    float* ha = c->h_small;
+    float* hm = c->h_small + c->small_cap;
+    WSO_CUDA(c, cudaMemcpyAsync(ha, c->d_ampl + first_slot, sizeof(float) * n, cudaMemcpyDeviceToHost, c->stream));
+    WSO_CUDA(c, cudaMemcpyAsync(hm, c->d_minmax + 2 * first_slot, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost, c->stream));
+    WSO_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (uint32_t i = 0; i < n; ++i) {
+        if (amplitude) amplitude[i] = ha[i];
+        if (min_height) min_height[i] = hm[2 * i];
+        if (max_height) max_height[i] = hm[2 * i + 1];
+    }
+    return WSO_OK;
+}
+
+int wso_compute(wso_ctx* c, float t, float* amplitude) {
+    int rc = check_batch(c, 1, nullptr, &t, 0);
+    if (rc != WSO_OK) return rc;
+    WSO_CUDA(c, cudaSetDevice(c->device));
+    if ((rc = push_lambdas(c)) != WSO_OK) return rc;
+    if ((rc = enqueue_chunk(c, 1, nullptr, &t, 0, 0)) != WSO_OK) return rc;
+    const size_t bytes = sizeof(float4) * (size_t)c->n * c->n;
+    WSO_CUDA(c, cudaMemcpyAsync(c->h_disp, c->d_disp, bytes, cudaMemcpyDeviceToHost, c->stream));
+    WSO_CUDA(c, cudaMemcpyAsync(c->h_norm, c->d_norm, bytes, cudaMemcpyDeviceToHost, c->stream));
+    WSO_CUDA(c, cudaMemcpyAsync(c->h_small, c->d_ampl, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    WSO_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (amplitude) *amplitude = c->h_small[0];
+    return WSO_OK;
+}
+
+int wso_compute_to_host(wso_ctx* c, uint32_t n, const uint32_t* tiles, const float* t, float* disp_host,
+                        float* norm_host, float* amplitude, float* min_height, float* max_height) {
+    if (!c) return WSO_ERR_INVALID_ARG;
+    if (!disp_host || !norm_host) return fail(c, WSO_ERR_INVALID_ARG, "host buffers are NULL");
+    // Slots are recycled: chunk k uses slots [ (k&1)*chunk , (k&1)*chunk + m ).
+    const uint32_t need = (n <= c->chunk) ? n : 2 * c->chunk;
+    if (need > c->max_slots) return fail(c, WSO_ERR_INVALID_ARG, "wso_compute_to_host needs max_slots >= 2*chunk");
+    int rc = check_batch(c, 0, nullptr, t, 0);
+    if (rc != WSO_OK) return rc;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t tl = tiles ? tiles[i] : 0u;
+        if (tl >= c->max_tiles) return fail(c, WSO_ERR_INVALID_ARG, "tile index out of range");
+        if (!c->tiles[tl].is_prepared) return fail(c, WSO_ERR_NOT_PREPARED, "Prepare() has not been called for this tile");
+    }
+    WSO_CUDA(c, cudaSetDevice(c->device));
+    if ((rc = push_lambdas(c)) != WSO_OK) return rc;
+    const size_t texels = (size_t)c->n * c->n;
+    const size_t map_bytes = sizeof(float4) * texels;
+    if (n > c->small_cap) {  // pinned staging for amplitude/min/max of every tile-frame
+        WSO_CUDA(c, cudaStreamSynchronize(c->stream));
+        cudaFreeHost(c->h_small);
+        c->h_small = nullptr;
+        c->small_cap = 0;
+        WSO_CUDA(c, cudaMallocHost(&c->h_small, sizeof(float) * 3 * n));
+        c->small_cap = n;
+    }
+    float* small = c->h_small;
+    int k = 0;
+    for (uint32_t done = 0; done < n; done += c->chunk, ++k) {
+        const uint32_t m = (n - done < c->chunk) ? (n - done) : c->chunk;
+        const int b = k & 1;
+        const uint32_t slot0 = (uint32_t)b * c->chunk;
+        // the slots (and W buffer) of parity b are free once the copy issued two chunks ago is done
+        if (k >= 2) WSO_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
+        rc = enqueue_chunk(c, m, tiles ? tiles + done : nullptr, t + done, slot0, b);
+        if (rc != WSO_OK) return rc;
+        WSO_CUDA(c, cudaEventRecord(c->ev_chunk[b], c->stream));
+        WSO_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_chunk[b], 0));
+        WSO_CUDA(c, cudaMemcpyAsync(disp_host + (size_t)done * texels * 4, c->d_disp + (size_t)slot0 * texels,
+                                    map_bytes * m, cudaMemcpyDeviceToHost, c->copy_stream));
+        WSO_CUDA(c, cudaMemcpyAsync(norm_host + (size_t)done * texels * 4, c->d_norm + (size_t)slot0 * texels,
+                                    map_bytes * m, cudaMemcpyDeviceToHost, c->copy_stream));
+        WSO_CUDA(c, cudaMemcpyAsync(small + done, c->d_ampl + slot0, sizeof(float) * m,
+                                    cudaMemcpyDeviceToHost, c->copy_stream));
+        WSO_CUDA(c, cudaMemcpyAsync(small + n + 2 * (size_t)done, c->d_minmax + 2 * slot0,
+                                    sizeof(float) * 2 * m, cudaMemcpyDeviceToHost, c->copy_stream));
+        WSO_CUDA(c, cudaEventRecord(c->ev_copied[b], c->copy_stream));
+    }
+    WSO_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+    WSO_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (uint32_t i = 0; i < n; ++i) {
+        if (amplitude) amplitude[i] = small[i];
+        if (min_height) min_height[i] = small[n + 2 * (size_t)i];
+        if (max_height) max_height[i] = small[n + 2 * (size_t)i + 1];
+    }
+    return WSO_OK;
+}
+
+int wso_map_host(wso_ctx* c, int which, const float** ptr, size_t* texels) {
+    if (!c || !ptr) return WSO_ERR_INVALID_ARG;
+    if (which != WSO_MAP_DISPLACEMENT && which != WSO_MAP_NORMAL) return fail(c, WSO_ERR_INVALID_ARG, "bad map id");
+    *ptr = reinterpret_cast<const float*>(which == WSO_MAP_DISPLACEMENT ? c->h_disp : c->h_norm);
+    if (texels) *texels = (size_t)c->n * c->n;
+    return WSO_OK;
+}
+
+int wso_map_device(wso_ctx* c, int which, uint32_t slot, void** dptr, size_t* texels) {
+    if (!c || !dptr) return WSO_ERR_INVALID_ARG;
+    if (which != WSO_MAP_DISPLACEMENT && which != WSO_MAP_NORMAL) return fail(c, WSO_ERR_INVALID_ARG, "bad map id");
+    if (slot >= c->max_slots) return fail(c, WSO_ERR_INVALID_ARG, "slot out of range");
+    const size_t n2 = (size_t)c->n * c->n;
+    *dptr = (which == WSO_MAP_DISPLACEMENT ? c->d_disp : c->d_norm) + n2 * slot;
+    if (texels) *texels = n2;
+    return WSO_OK;
+}
+
+int wso_copy_map(wso_ctx* c, int which, uint32_t slot, float* dst) {
+    void* src = nullptr;
+    size_t texels = 0;
+    int rc = wso_map_device(c, which, slot, &src, &texels);
+    if (rc != WSO_OK) return rc;
+    if (!dst) return fail(c, WSO_ERR_INVALID_ARG, "dst is NULL");
+    WSO_CUDA(c, cudaSetDevice(c->device));
+    WSO_CUDA(c, cudaMemcpyAsync(dst, src, sizeof(float4) * texels, cudaMemcpyDeviceToHost, c->stream));
+    WSO_CUDA(c, cudaStreamSynchronize(c->stream));
+    return WSO_OK;
+}
+
+int wso_set_stream(wso_ctx* c, void* cuda_stream) {
+    if (!c) return WSO_ERR_INVALID_ARG;
+    WSO_CUDA(c, cudaSetDevice(c->device));
+    WSO_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+    return WSO_OK;
+}
+
+int wso_alloc_host(size_t bytes, void** ptr) {
+    if (!ptr) return WSO_ERR_INVALID_ARG;
+    cudaError_t e = cudaMallocHost(ptr, bytes);
+    if (e != cudaSuccess) return fail_cuda(nullptr, e, "cudaMallocHost");
+    return WSO_OK;
+}
+
+int wso_free_host(void* ptr) {
+    cudaError_t e = cudaFreeHost(ptr);
+    return e == cudaSuccess ? WSO_OK : WSO_ERR_CUDA;
+}
+
+int wso_set_profiling(wso_ctx* c, int on) {
+    if (!c) return WSO_ERR_INVALID_ARG;
+    WSO_CUDA(c, cudaSetDevice(c->device));
+    WSO_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->profiling = on != 0;
+    c->prof_used = 0;
+    c->prof_ms[0] = c->prof_ms[1] = c->prof_ms[2] = 0.0;
+    c->prof_launches = 0;
+    c->prof_items = 0;
+    return WSO_OK;
+}
+
+int wso_get_profile(wso_ctx* c, double* kernel_ms, uint64_t* launches, uint64_t* tile_frames) {
+    if (!c) return WSO_ERR_INVALID_ARG;
+    WSO_CUDA(c, cudaSetDevice(c->device));
+    WSO_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i + 3 < c->prof_used; i += 4)
+        for (int k = 0; k < 3; ++k) {
+            float ms = 0.0f;
+            WSO_CUDA(c, cudaEventElapsedTime(&ms, c->prof_events[i + k], c->prof_events[i + k + 1]));
+            c->prof_ms[k] += (double)ms;
+        }
+    c->prof_used = 0;
+    if (kernel_ms) for (int k = 0; k < 3; ++k) kernel_ms[k] = c->prof_ms[k];
+    if (launches) *launches = c->prof_launches;
+    if (tile_frames) *tile_frames = c->prof_items;
+    return WSO_OK;
+}
+
+int wso_get_stats(const wso_ctx* c, uint64_t* kernel_launches, uint32_t* chunk) {
+    if (!c) return WSO_ERR_INVALID_ARG;
+    if (kernel_launches) *kernel_launches = c->launches;
+    if (chunk) *chunk = c->chunk;
+    return WSO_OK;
+}
+
+const char* wso_last_error(const wso_ctx* c) {
+    if (c) return c->err.c_str();
+    std::lock_guard<std::mutex> lk(g_err_mutex);
+    static thread_local std::string copy;
+    copy = g_create_error;
+    return copy.c_str();
+}
+
+const char* wso_version(void) { return "wsocean 0.1 (sm_100a)"; }
+
+}  // extern "C"

@@ -1,0 +1,309 @@
+// wso_device.cuh — building blocks shared by the sm_100a kernels.
+//
+// Everything here is written as plain "per-thread body" code behind two tiny executor types
+// (DeviceExec / HostExec) so that the SAME kernel bodies can also be compiled by g++ and stepped
+// thread-by-thread on the CPU by tests/emu (index/layout debugging without a GPU).  The host build
+// is test infrastructure only; the product library contains the CUDA build exclusively.
+#pragma once
+
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#include <cuda_runtime.h>
+#define WSO_HD __host__ __device__ __forceinline__
+#else
+#include <cmath>
+#define WSO_HD inline
+struct float2 {
+    float x, y;
+};
+struct alignas(16) float4 {
+    float x, y, z, w;
+};
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+#endif
+
+namespace wso {
+
+// ---------------------------------------------------------------------------------------------
+// fp32 helpers.  wso_mul/add/sub are NEVER contracted into FMAs: the spectrum-evolve step mirrors
+// the reference's x86 (non-FMA) rounding order (reference: WSTessendorf.h:265-275, cpp:303-336).
+// ---------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+WSO_HD float rmul(float a, float b) { return __fmul_rn(a, b); }
+WSO_HD float radd(float a, float b) { return __fadd_rn(a, b); }
+WSO_HD float rsub(float a, float b) { return __fsub_rn(a, b); }
+WSO_HD float rsqrt_ieee(float a) { return __fdiv_rn(1.0f, __fsqrt_rn(a)); }
+WSO_HD float sqrt_ieee(float a) { return __fsqrt_rn(a); }
+WSO_HD void sincos_acc(float x, float* s, float* c) { sincosf(x, s, c); }
+#else
+WSO_HD float rmul(float a, float b) { return a * b; }
+WSO_HD float radd(float a, float b) { return a + b; }
+WSO_HD float rsub(float a, float b) { return a - b; }
+WSO_HD float rsqrt_ieee(float a) { return 1.0f / std::sqrt(a); }
+WSO_HD float sqrt_ieee(float a) { return std::sqrt(a); }
+WSO_HD void sincos_acc(float x, float* s, float* c) {
+    *s = std::sin(x);
+    *c = std::cos(x);
+}
+#endif
+
+WSO_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+WSO_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+WSO_HD float2 cmul(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+WSO_HD float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+
+// ---------------------------------------------------------------------------------------------
+// Shared-memory line layout: logical element i of an FFT line lives at pad_idx(i).
+// One float2 of padding per 16 elements makes every access pattern of the Stockham stages below
+// (unit stride, stride R0 after the first stage, 16-element groups afterwards) bank-conflict free
+// for 64-bit accesses (tools/bank_conflicts.py).
+// ---------------------------------------------------------------------------------------------
+WSO_HD int pad_idx(int i) { return i + (i >> 4); }
+template <int N>
+struct LineStride {
+    // +4 keeps consecutive lines 4 (64-bit) banks apart: the pass-1 store phase reads the same
+    // element of 4 adjacent lines in one request.
+    static constexpr int value = N + (N >> 4) + 4;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Radix plans (Stockham autosort, decimation in time).  Product of radices == N.
+// First radix <= 8 or 16 with second radix 16 keeps all smem traffic conflict free.
+// ---------------------------------------------------------------------------------------------
+template <int LOGN>
+struct Plan;
+template <> struct Plan<4>  { static constexpr int S = 1; static constexpr int R[4] = {16, 1, 1, 1}; };
+template <> struct Plan<5>  { static constexpr int S = 2; static constexpr int R[4] = {2, 16, 1, 1}; };
+template <> struct Plan<6>  { static constexpr int S = 2; static constexpr int R[4] = {4, 16, 1, 1}; };
+template <> struct Plan<7>  { static constexpr int S = 2; static constexpr int R[4] = {8, 16, 1, 1}; };
+template <> struct Plan<8>  { static constexpr int S = 2; static constexpr int R[4] = {16, 16, 1, 1}; };
+template <> struct Plan<9>  { static constexpr int S = 3; static constexpr int R[4] = {2, 16, 16, 1}; };
+template <> struct Plan<10> { static constexpr int S = 3; static constexpr int R[4] = {4, 16, 16, 1}; };
+template <> struct Plan<11> { static constexpr int S = 3; static constexpr int R[4] = {8, 16, 16, 1}; };
+template <> struct Plan<12> { static constexpr int S = 3; static constexpr int R[4] = {16, 16, 16, 1}; };
+template <> struct Plan<13> { static constexpr int S = 4; static constexpr int R[4] = {2, 16, 16, 16}; };
+template <> struct Plan<14> { static constexpr int S = 4; static constexpr int R[4] = {4, 16, 16, 16}; };
+
+// ---------------------------------------------------------------------------------------------
+// Small in-register DFTs, backward sign: X[k] = sum_n x[n] exp(+2*pi*i*n*k/R), natural order.
+// ---------------------------------------------------------------------------------------------
+// multiply by exp(+2*pi*i*E/16), E compile-time
+template <int E>
+WSO_HD float2 mul_w16(float2 a) {
+    constexpr int e = E & 15;
+    if (e == 0) return a;
+    if (e == 4) return make_float2(-a.y, a.x);
+    if (e == 8) return make_float2(-a.x, -a.y);
+    if (e == 12) return make_float2(a.y, -a.x);
+    constexpr float h = 0.70710678118654752440f;
+    if (e == 2) return make_float2(h * (a.x - a.y), h * (a.x + a.y));
+    if (e == 6) return make_float2(h * (-a.x - a.y), h * (a.x - a.y));
+    if (e == 10) return make_float2(h * (a.y - a.x), h * (-a.x - a.y));
+    if (e == 14) return make_float2(h * (a.x + a.y), h * (a.y - a.x));
+    constexpr float c1 = 0.92387953251128675613f;  // cos(pi/8)
+    constexpr float s1 = 0.38268343236508977173f;  // sin(pi/8)
+    // remaining odd e: (cos, sin) of e*pi/8
+    constexpr float wc = (e == 1) ? c1 : (e == 3) ? s1 : (e == 5) ? -s1 : (e == 7) ? -c1
+                       : (e == 9) ? -c1 : (e == 11) ? -s1 : (e == 13) ? s1 : c1;
+    constexpr float ws = (e == 1) ? s1 : (e == 3) ? c1 : (e == 5) ? c1 : (e == 7) ? s1
+                       : (e == 9) ? -s1 : (e == 11) ? -c1 : (e == 13) ? -c1 : -s1;
+    return make_float2(a.x * wc - a.y * ws, a.x * ws + a.y * wc);
+}
+
+WSO_HD void dft2(float2& a, float2& b) {
+    const float2 t = a;
+    a = cadd(t, b);
+    b = csub(t, b);
+}
+// in-place on 4 named values, natural order out
+WSO_HD void dft4(float2& x0, float2& x1, float2& x2, float2& x3) {
+    const float2 s0 = cadd(x0, x2), d0 = csub(x0, x2);
+    const float2 s1 = cadd(x1, x3), d1 = csub(x1, x3);
+    const float2 id1 = make_float2(-d1.y, d1.x);  // i * d1
+    x0 = cadd(s0, s1);
+    x1 = cadd(d0, id1);
+    x2 = csub(s0, s1);
+    x3 = csub(d0, id1);
+}
+
+template <int R>
+struct Dft;
+template <> struct Dft<1> { static WSO_HD void run(float2*) {} };
+template <> struct Dft<2> { static WSO_HD void run(float2* v) { dft2(v[0], v[1]); } };
+template <> struct Dft<4> { static WSO_HD void run(float2* v) { dft4(v[0], v[1], v[2], v[3]); } };
+template <> struct Dft<8> {
+    static WSO_HD void run(float2* v) {
+        // radix-2 x radix-4 (DIT): E = DFT4(even), O = DFT4(odd), X[k] = E[k] + w8^k O[k]
+        dft4(v[0], v[2], v[4], v[6]);
+        dft4(v[1], v[3], v[5], v[7]);
+        const float2 o0 = v[1], o1 = mul_w16<2>(v[3]), o2 = mul_w16<4>(v[5]), o3 = mul_w16<6>(v[7]);
+        const float2 e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6];
+        v[0] = cadd(e0, o0); v[4] = csub(e0, o0);
+        v[1] = cadd(e1, o1); v[5] = csub(e1, o1);
+        v[2] = cadd(e2, o2); v[6] = csub(e2, o2);
+        v[3] = cadd(e3, o3); v[7] = csub(e3, o3);
+    }
+};
+template <> struct Dft<16> {
+    static WSO_HD void run(float2* v) {
+        // radix-4 x radix-4 (DIT): Y_a = DFT4 over b of x[a+4b]; X[k1+4k2] = DFT4 over a of w16^(a k1) Y_a[k1]
+        dft4(v[0], v[4], v[8], v[12]);
+        dft4(v[1], v[5], v[9], v[13]);
+        dft4(v[2], v[6], v[10], v[14]);
+        dft4(v[3], v[7], v[11], v[15]);
+        // Y_a[k1] now sits in v[a + 4*k1]
+        v[5] = mul_w16<1>(v[5]);   v[6] = mul_w16<2>(v[6]);    v[7] = mul_w16<3>(v[7]);
+        v[9] = mul_w16<2>(v[9]);   v[10] = mul_w16<4>(v[10]);  v[11] = mul_w16<6>(v[11]);
+        v[13] = mul_w16<3>(v[13]); v[14] = mul_w16<6>(v[14]);  v[15] = mul_w16<9>(v[15]);
+        dft4(v[0], v[1], v[2], v[3]);      // k1 = 0 -> X[0], X[4], X[8], X[12]
+        dft4(v[4], v[5], v[6], v[7]);      // k1 = 1 -> X[1], X[5], X[9], X[13]
+        dft4(v[8], v[9], v[10], v[11]);    // k1 = 2
+        dft4(v[12], v[13], v[14], v[15]);  // k1 = 3
+        // v[4*k1 + k2] = X[k1 + 4*k2]  -> transpose the 4x4 to natural order
+        float2 t;
+        t = v[1];  v[1] = v[4];   v[4] = t;
+        t = v[2];  v[2] = v[8];   v[8] = t;
+        t = v[3];  v[3] = v[12];  v[12] = t;
+        t = v[6];  v[6] = v[9];   v[9] = t;
+        t = v[7];  v[7] = v[13];  v[13] = t;
+        t = v[11]; v[11] = v[14]; v[14] = t;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Executors.  each(f): run f(tid, state) for every thread of the CTA.  sync(): CTA barrier.
+// ---------------------------------------------------------------------------------------------
+static constexpr int kValsPerThread = 16;  // complex values a thread carries between barriers
+
+struct ThreadState {
+    float2 v[kValsPerThread];
+};
+
+#if defined(__CUDACC__)
+struct DeviceExec {
+    ThreadState st;
+    template <class F>
+    __device__ __forceinline__ void each(F&& f) {
+        f((int)threadIdx.x, st);
+    }
+    __device__ __forceinline__ void sync() { __syncthreads(); }
+
+    // Fold the (min,max) every thread left in st.v[0] into out[0] (min) / out[1] (max):
+    // warp-shuffle butterfly, then one pair of atomics per warp.  Float ordering through the
+    // sign-aware int/uint trick, valid for any mix of signs.
+    __device__ __forceinline__ void commit_minmax(float* out) {
+        float mn = st.v[0].x, mx = st.v[0].y;
+        const bool full_warps = (blockDim.x & 31u) == 0u;
+        if (full_warps) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            }
+        }
+        if (!full_warps || (threadIdx.x & 31u) == 0u) {
+            if (mn >= 0.0f) atomicMin(reinterpret_cast<int*>(out), __float_as_int(mn));
+            else atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(mn));
+            if (mx >= 0.0f) atomicMax(reinterpret_cast<int*>(out + 1), __float_as_int(mx));
+            else atomicMin(reinterpret_cast<unsigned int*>(out + 1), __float_as_uint(mx));
+        }
+    }
+};
+#endif
+
+struct HostExec {
+    int nthreads;
+    ThreadState* states;  // [nthreads]
+    template <class F>
+    void each(F&& f) {
+        for (int t = 0; t < nthreads; ++t) f(t, states[t]);
+    }
+    void sync() {}
+    void commit_minmax(float* out) {
+        for (int t = 0; t < nthreads; ++t) {
+            if (states[t].v[0].x < out[0]) out[0] = states[t].v[0].x;
+            if (states[t].v[0].y > out[1]) out[1] = states[t].v[0].y;
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// One Stockham stage over B lines of length N held in shared memory (in place: all loads, barrier,
+// butterflies + stores, barrier).  CTA size T = B*N/16; every thread carries 16 values.
+//   radix R, NS = product of the radices of the earlier stages.
+//   load : v[r] = x[j + r*N/R]                         (unit stride across threads)
+//   twid : v[r] *= w_{NS*R}^{(j % NS) * r}
+//   store: y[(j/NS)*NS*R + (j%NS) + r*NS] = DFT_R(v)[r]
+// ---------------------------------------------------------------------------------------------
+template <int N, int B, int R, int NS>
+struct Stage {
+    static constexpr int T = B * N / kValsPerThread;
+    static constexpr int NB = kValsPerThread / R;  // butterflies per thread
+    static constexpr int LS = LineStride<N>::value;
+    static constexpr int JN = N / R;               // butterflies per line
+
+    static WSO_HD void load(const float2* smem, int tid, ThreadState& st) {
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            const int u = tid + T * i;
+            const int line = u / JN;
+            const int j = u % JN;
+            const float2* x = smem + line * LS;
+#pragma unroll
+            for (int r = 0; r < R; ++r) st.v[i * R + r] = x[pad_idx(j + r * JN)];
+        }
+    }
+
+    static WSO_HD void twiddle_dft(const float2* __restrict__ tw, int tid, ThreadState& st) {
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            if (NS > 1) {
+                const int u = tid + T * i;
+                const int j = u % JN;
+                const int k = j % NS;
+                constexpr int tstep = N / (NS * R);
+#pragma unroll
+                for (int r = 1; r < R; ++r) st.v[i * R + r] = cmul(st.v[i * R + r], tw[tstep * k * r]);
+            }
+            Dft<R>::run(&st.v[i * R]);
+        }
+    }
+
+    static WSO_HD void store(float2* smem, int tid, const ThreadState& st) {
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            const int u = tid + T * i;
+            const int line = u / JN;
+            const int j = u % JN;
+            const int k = j % NS;
+            const int base = (j / NS) * NS * R + k;
+            float2* y = smem + line * LS;
+#pragma unroll
+            for (int r = 0; r < R; ++r) y[pad_idx(base + r * NS)] = st.v[i * R + r];
+        }
+    }
+};
+
+// Runs stages FIRST..S-1 of Plan<LOGN> on data already in smem (natural order in, natural order out).
+template <int LOGN, int B, int SI, int NS, class Exec>
+struct RunStages {
+    static WSO_HD void run(Exec& ex, float2* smem, const float2* __restrict__ tw) {
+        constexpr int N = 1 << LOGN;
+        constexpr int R = Plan<LOGN>::R[SI];
+        using St = Stage<N, B, R, NS>;
+        ex.each([&](int tid, ThreadState& st) { St::load(smem, tid, st); });
+        ex.sync();
+        ex.each([&](int tid, ThreadState& st) {
+            St::twiddle_dft(tw, tid, st);
+            St::store(smem, tid, st);
+        });
+        ex.sync();
+        if constexpr (SI + 1 < Plan<LOGN>::S) RunStages<LOGN, B, SI + 1, NS * R, Exec>::run(ex, smem, tw);
+    }
+};
+
+}  // namespace wso
