@@ -105,56 +105,86 @@ static inline T* fft_lines(T* x, T* y, int n, const Twiddles<T>& tw) {
     return x;
 }
 
-/* In-place 2-D transform of an n0 x n1 row-major complex<float> array, computed in type T.
- * For T=double every intermediate (including the array between the two passes) is float64. */
+/* Plan for an in-place 2-D transform of an n0 x n1 row-major complex<float> array, computed in type T.
+ * For T=double every intermediate (including the array between the two passes) is float64 and the result
+ * is rounded once to fp32; for T=float the data are transformed in place.  Twiddles and scratch live in
+ * the plan (like an FFTW plan), so execute() allocates nothing. */
+template <typename T, int B>
+struct Plan2D {
+    int n0 = 0, n1 = 0, sign = +1;
+    Twiddles<T> tw0, tw1;
+    std::vector<T> bx, by, work;
+
+    void init(int n0_, int n1_, int sign_) {
+        n0 = n0_; n1 = n1_; sign = sign_;
+        tw0.init(n0, sign);
+        tw1.init(n1, sign);
+        const int nmax = n0 > n1 ? n0 : n1;
+        bx.resize((size_t)2 * B * nmax);
+        by.resize((size_t)2 * B * nmax);
+        if (sizeof(T) != sizeof(float)) work.resize((size_t)2 * n0 * n1);
+    }
+
+    template <typename U>
+    void passes(U* w) {
+        // rows (transform along n1): B rows at a time, interleaved [n][b]
+        for (int r0 = 0; r0 < n0; r0 += B) {
+            const int nb = (n0 - r0) < B ? (n0 - r0) : B;
+            for (int b = 0; b < B; ++b) {
+                const U* src = w + 2 * (size_t)(r0 + (b < nb ? b : 0)) * n1;
+                T* dst = bx.data() + 2 * b;
+                for (int n = 0; n < n1; ++n) {
+                    dst[2 * (size_t)n * B] = (T)src[2 * n];
+                    dst[2 * (size_t)n * B + 1] = (T)src[2 * n + 1];
+                }
+            }
+            const T* res = fft_lines<T, B>(bx.data(), by.data(), n1, tw1);
+            for (int b = 0; b < nb; ++b) {
+                U* dst = w + 2 * (size_t)(r0 + b) * n1;
+                const T* src = res + 2 * b;
+                for (int n = 0; n < n1; ++n) {
+                    dst[2 * n] = (U)src[2 * (size_t)n * B];
+                    dst[2 * n + 1] = (U)src[2 * (size_t)n * B + 1];
+                }
+            }
+        }
+        // columns (transform along n0): B adjacent columns are already interleaved in memory
+        for (int c0 = 0; c0 < n1; c0 += B) {
+            const int nb = (n1 - c0) < B ? (n1 - c0) : B;
+            for (int m = 0; m < n0; ++m) {
+                const U* src = w + 2 * ((size_t)m * n1 + c0);
+                T* dst = bx.data() + 2 * (size_t)m * B;
+                for (int i = 0; i < 2 * nb; ++i) dst[i] = (T)src[i];
+                for (int i = 2 * nb; i < 2 * B; ++i) dst[i] = (T)0;
+            }
+            const T* res = fft_lines<T, B>(bx.data(), by.data(), n0, tw0);
+            for (int m = 0; m < n0; ++m) {
+                U* dst = w + 2 * ((size_t)m * n1 + c0);
+                const T* src = res + 2 * (size_t)m * B;
+                for (int i = 0; i < 2 * nb; ++i) dst[i] = (U)src[i];
+            }
+        }
+    }
+
+    void execute(std::complex<float>* data) {
+        float* d = reinterpret_cast<float*>(data);
+        if (sizeof(T) == sizeof(float)) {
+            passes<float>(d);
+        } else {
+            const size_t cnt = (size_t)2 * n0 * n1;
+            for (size_t i = 0; i < cnt; ++i) work[i] = (T)d[i];
+            passes<T>(work.data());
+            for (size_t i = 0; i < cnt; ++i) d[i] = (float)work[i];
+        }
+    }
+};
+
+/* One-shot convenience wrapper (plans on every call). */
 template <typename T, int B>
 static void fft2d(std::complex<float>* data, int n0, int n1, int sign) {
-    Twiddles<T> tw0, tw1;
-    tw0.init(n0, sign);
-    tw1.init(n1, sign);
-    std::vector<T> work((size_t)2 * n0 * n1);
-    for (size_t i = 0; i < (size_t)n0 * n1; ++i) {
-        work[2 * i] = (T)data[i].real();
-        work[2 * i + 1] = (T)data[i].imag();
-    }
-    const int nmax = n0 > n1 ? n0 : n1;
-    std::vector<T> bx((size_t)2 * B * nmax), by((size_t)2 * B * nmax);
-    // rows (transform along n1)
-    for (int r0 = 0; r0 < n0; r0 += B) {
-        const int nb = (n0 - r0) < B ? (n0 - r0) : B;
-        for (int n = 0; n < n1; ++n)
-            for (int b = 0; b < B; ++b) {
-                const size_t src = (size_t)(r0 + (b < nb ? b : 0)) * n1 + n;
-                bx[2 * ((size_t)n * B + b)] = work[2 * src];
-                bx[2 * ((size_t)n * B + b) + 1] = work[2 * src + 1];
-            }
-        T* res = fft_lines<T, B>(bx.data(), by.data(), n1, tw1);
-        for (int n = 0; n < n1; ++n)
-            for (int b = 0; b < nb; ++b) {
-                const size_t dst = (size_t)(r0 + b) * n1 + n;
-                work[2 * dst] = res[2 * ((size_t)n * B + b)];
-                work[2 * dst + 1] = res[2 * ((size_t)n * B + b) + 1];
-            }
-    }
-    // columns (transform along n0)
-    for (int c0 = 0; c0 < n1; c0 += B) {
-        const int nb = (n1 - c0) < B ? (n1 - c0) : B;
-        for (int m = 0; m < n0; ++m)
-            for (int b = 0; b < B; ++b) {
-                const size_t src = (size_t)m * n1 + c0 + (b < nb ? b : 0);
-                bx[2 * ((size_t)m * B + b)] = work[2 * src];
-                bx[2 * ((size_t)m * B + b) + 1] = work[2 * src + 1];
-            }
-        T* res = fft_lines<T, B>(bx.data(), by.data(), n0, tw0);
-        for (int m = 0; m < n0; ++m)
-            for (int b = 0; b < nb; ++b) {
-                const size_t dst = (size_t)m * n1 + c0 + b;
-                work[2 * dst] = res[2 * ((size_t)m * B + b)];
-                work[2 * dst + 1] = res[2 * ((size_t)m * B + b) + 1];
-            }
-    }
-    for (size_t i = 0; i < (size_t)n0 * n1; ++i)
-        data[i] = std::complex<float>((float)work[2 * i], (float)work[2 * i + 1]);
+    Plan2D<T, B> p;
+    p.init(n0, n1, sign);
+    p.execute(data);
 }
 
 }  // namespace wso_cpu_fft

@@ -35,7 +35,9 @@ struct wso_shim_plan_s {
     int n0, n1, sign;
     fftwf_complex* in;
     fftwf_complex* out;
-    void* real_plan;  // mode 3
+    void* real_plan;                          // mode 3
+    wso_cpu_fft::Plan2D<float, 16>* fast;     // mode 1 (twiddles + scratch planned once, like FFTW)
+    wso_cpu_fft::Plan2D<double, 8>* exact;    // mode 0
 };
 
 static int g_fft_mode = 0;
@@ -77,7 +79,7 @@ void fftwf_free(void* p) { free(p); }
 
 fftwf_plan fftwf_plan_dft_2d(int n0, int n1, fftwf_complex* in, fftwf_complex* out, int sign,
                              unsigned flags) {
-    wso_shim_plan_s* p = new wso_shim_plan_s{n0, n1, sign, in, out, nullptr};
+    wso_shim_plan_s* p = new wso_shim_plan_s{n0, n1, sign, in, out, nullptr, nullptr, nullptr};
     if (g_fft_mode == 3 && g_real.load())
         p->real_plan = g_real.plan_dft_2d(n0, n1, in, out, sign, flags);
     return p;
@@ -92,14 +94,27 @@ void fftwf_execute(const fftwf_plan p) {
     if (p->in != p->out)
         std::memcpy(p->out, p->in, sizeof(fftwf_complex) * (size_t)p->n0 * p->n1);
     std::complex<float>* d = reinterpret_cast<std::complex<float>*>(p->out);
-    if (g_fft_mode == 1)
-        wso_cpu_fft::fft2d<float, 16>(d, p->n0, p->n1, p->sign);
-    else
-        wso_cpu_fft::fft2d<double, 8>(d, p->n0, p->n1, p->sign);
+    if (g_fft_mode == 1) {
+        if (!p->fast) {
+            p->fast = new wso_cpu_fft::Plan2D<float, 16>();
+            p->fast->init(p->n0, p->n1, p->sign);
+        }
+        p->fast->execute(d);
+    } else {
+        if (!p->exact) {
+            p->exact = new wso_cpu_fft::Plan2D<double, 8>();
+            p->exact->init(p->n0, p->n1, p->sign);
+        }
+        p->exact->execute(d);
+    }
 }
 
 void fftwf_destroy_plan(fftwf_plan p) {
     if (p && p->real_plan) g_real.destroy_plan(p->real_plan);
+    if (p) {
+        delete p->fast;
+        delete p->exact;
+    }
     delete p;
 }
 

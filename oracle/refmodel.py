@@ -31,8 +31,17 @@ FFT_REAL_FFTW = 3  # dlopen("libfftw3f.so.3") when the box has one
 _lib = None
 
 
+def _cpu_has_avx2() -> bool:
+    try:
+        with open("/proc/cpuinfo") as f:
+            return " avx2" in f.read()
+    except OSError:
+        return False
+
+
 def available() -> bool:
-    return os.path.exists(REF_LIB_PATH)
+    """The shim FFT inside libwsref.so is built with -mavx2 (oracle/Makefile)."""
+    return os.path.exists(REF_LIB_PATH) and _cpu_has_avx2()
 
 
 def lib():
