@@ -259,7 +259,10 @@ def main():
         ws.SetWindSpeed(prm["speed"], j)
         # every rank owns its own realisation (independent tiles / its share of the animation)
         ws.PrepareWithGauss(gauss(n, wl["seed"] + j + 7919 * rank), tile=j)
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-default) torch stream carries every kernel, so torch.cuda.Event brackets them
+    stream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ws.set_stream(stream.cuda_stream)
 
     def barrier():

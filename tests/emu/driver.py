@@ -23,14 +23,16 @@ def lib():
                                    "-I", CSRC, "-o", LIB, os.path.join(HERE, "emu.cpp")])
         L = C.CDLL(LIB)
         vp = C.c_void_p
-        L.wso_emu_compute.argtypes = [C.c_int, C.c_int, vp, vp, vp, C.c_float, C.c_float, vp, vp, vp, vp, vp]
+        L.wso_emu_compute.argtypes = [C.c_int, C.c_int, vp, vp, vp, C.c_float, C.c_float, C.c_float, vp, vp, vp, vp,
+                                      vp]
         L.wso_emu_compute.restype = C.c_int
         _lib = L
     return _lib
 
 
-def compute(n, tile_length, lam, h0_re, h0_im, omega, t, variant=0, want_w=False):
-    """Run emulated K1+K2+K3 for one tile-frame. h0_* are (N,N) row-major [m][n] (reference layout)."""
+def compute(n, tile_length, lam, h0_re, h0_im, omega, t, variant=0, want_w=False, anim_period=200.0):
+    """Run emulated K1+K2+K3 for one tile-frame. h0_* are (N,N) row-major [m][n] (reference layout).
+    anim_period=None forces the direct sincosf path; otherwise the sincos table is used when omega allows."""
     logn = int(np.log2(n))
     amp_t = np.ascontiguousarray(np.stack([h0_re.T, h0_im.T], axis=-1).astype(np.float32))
     om_t = np.ascontiguousarray(omega.T.astype(np.float32))
@@ -43,8 +45,10 @@ def compute(n, tile_length, lam, h0_re, h0_im, omega, t, variant=0, want_w=False
     a = np.zeros(1, np.float32)
     w = np.zeros((n // 2, 4, n), np.complex64) if want_w else None
     p = lambda x: None if x is None else x.ctypes.data_as(C.c_void_p)
-    rc = lib().wso_emu_compute(logn, variant, p(amp_t), p(om_t), p(kv), float(lam), float(t), p(disp), p(norm),
-                               p(mm), p(a), p(w))
+    omega0 = 0.0 if anim_period is None else float(
+        np.float32(np.float64(np.float32(2.0)) * np.pi / np.float64(np.float32(anim_period))))
+    rc = lib().wso_emu_compute(logn, variant, p(amp_t), p(om_t), p(kv), omega0, float(lam), float(t), p(disp),
+                               p(norm), p(mm), p(a), p(w))
     if rc != 0:
         raise ValueError(f"no emulated configuration for logn={logn} variant={variant}")
     return a[0], disp, norm, mm[0], mm[1], w

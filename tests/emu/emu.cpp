@@ -12,8 +12,8 @@
 using namespace wso;
 
 template <int LOGN, int CP, int NF, int RI>
-static int run_cfg(const float* amp_t, const float* omega_t, const float* kv, float lambda, float t,
-                   float* disp, float* norm, float* minmax, float* amp_out, float* w_out) {
+static int run_cfg(const float* amp_t, const float* omega_t, const float* kv, float omega0, float lambda,
+                   float t, float* disp, float* norm, float* minmax, float* amp_out, float* w_out) {
     constexpr int N = 1 << LOGN, H = N / 2;
     using P1 = Pass1<LOGN, CP, NF>;
     using P2 = Pass2<LOGN, RI>;
@@ -22,11 +22,33 @@ static int run_cfg(const float* amp_t, const float* omega_t, const float* kv, fl
         const double a = 2.0 * 3.14159265358979323846 * k / N;
         tw[k] = make_float2((float)cos(a), (float)sin(a));
     }
+    // same record / table decision as upload_h0() in wso_api.cu (omega0 <= 0: force the direct sincos path)
+    std::vector<float4> rec((size_t)N * N);
+    int jmax = 0;
+    bool table_ok = omega0 > 0.0f;
+    for (size_t i = 0; i < (size_t)N * N && table_ok; ++i) {
+        const float jf = std::nearbyint(omega_t[i] / omega0);
+        if (!(jf >= 0.0f && jf < (float)kMaxTable) || jf * omega0 != omega_t[i]) table_ok = false;
+        else if ((int)jf > jmax) jmax = (int)jf;
+    }
+    for (int n = 0; n < N; ++n)
+        for (int m = 0; m < N; ++m) {
+            const size_t i = (size_t)n * N + m;
+            const float d = kv[n] * kv[n] + kv[m] * kv[m];
+            const float inv = std::sqrt(d) > 0.00001f ? 1.0f / std::sqrt(d) : 0.0f;
+            float wf = omega_t[i];
+            if (table_ok) {
+                const int j = (int)std::nearbyint(omega_t[i] / omega0);
+                std::memcpy(&wf, &j, 4);
+            }
+            rec[i] = make_float4(amp_t[2 * i], amp_t[2 * i + 1], inv, wf);
+        }
     TileDev td;
-    td.amp = reinterpret_cast<const float2*>(amp_t);
-    td.omega = omega_t;
+    td.h0 = rec.data();
     td.kv = kv;
     td.lambda = lambda;
+    td.omega0 = omega0;
+    td.table_len = table_ok ? jmax + 1 : 0;
     td.pad_ = 0;
     std::vector<float2> W((size_t)H * 4 * N);
     LaunchArgs args;
@@ -70,10 +92,10 @@ static int run_cfg(const float* amp_t, const float* omega_t, const float* kv, fl
 }
 
 extern "C" int wso_emu_compute(int logn, int variant, const float* amp_t, const float* omega_t,
-                               const float* kv, float lambda, float t, float* disp, float* norm,
+                               const float* kv, float omega0, float lambda, float t, float* disp, float* norm,
                                float* minmax, float* amp_out, float* w_out) {
 #define CFG(L, V, CP, NF, RI) \
-    if (logn == L && variant == V) return run_cfg<L, CP, NF, RI>(amp_t, omega_t, kv, lambda, t, disp, norm, minmax, amp_out, w_out);
+    if (logn == L && variant == V) return run_cfg<L, CP, NF, RI>(amp_t, omega_t, kv, omega0, lambda, t, disp, norm, minmax, amp_out, w_out);
     CFG(4, 0, 8, 4, 8)
     CFG(4, 1, 2, 1, 1)
     CFG(5, 0, 8, 4, 8)
@@ -86,6 +108,7 @@ extern "C" int wso_emu_compute(int logn, int variant, const float* amp_t, const 
     CFG(9, 0, 4, 4, 4)
     CFG(9, 1, 4, 2, 2)
     CFG(10, 0, 4, 2, 4)
+    CFG(11, 0, 4, 1, 2)
 #undef CFG
     return -1;
 }

@@ -21,7 +21,13 @@ def test_emulated_kernels_vs_reference_fixture(name, variants):
     for v in variants:
         for i, t in enumerate(g["t"]):
             a, disp, norm, mn, mx, _ = E.compute(params["tile_size"], params["tile_length"], params["lam"],
-                                                 h0[..., 0], h0[..., 1], h0[..., 4], float(t), variant=v)
+                                                 h0[..., 0], h0[..., 1], h0[..., 4], float(t), variant=v,
+                                                 anim_period=params["anim_period"])
+            # the per-frame sincos table must be bit-identical to per-point sincosf
+            a2, disp2, norm2, _, _, _ = E.compute(params["tile_size"], params["tile_length"], params["lam"],
+                                                  h0[..., 0], h0[..., 1], h0[..., 4], float(t), variant=v,
+                                                  anim_period=None)
+            assert a == a2 and disp.tobytes() == disp2.tobytes() and norm.tobytes() == norm2.tobytes()
             assert_maps_close(disp, norm, g["disp"][i], g["norm"][i], f"{name} v{v} t={t}")
             assert abs(a - g["A"][i]) <= SCALAR_REL_TOL * g["A"][i]
             assert abs(mn - g["minh"][i]) <= SCALAR_REL_TOL * g["A"][i]

@@ -45,8 +45,7 @@ struct wso_ctx {
     uint64_t launches = 0;
     std::vector<Tile> tiles;
     // device
-    float2* d_amp = nullptr;     // [tile][n][m]
-    float* d_omega = nullptr;    // [tile][n][m]
+    float4* d_h0 = nullptr;      // [tile][n][m] (amp.re, amp.im, 1/|k|, omega or j)
     float* d_kv = nullptr;       // [tile][N]
     TileDev* d_tiles = nullptr;  // [tile]
     float2* d_tw = nullptr;      // [N]
@@ -112,8 +111,7 @@ bool valid_params(const wso_params& p) {
 }
 
 void free_device_buffers(wso_ctx* c) {
-    cudaFree(c->d_amp); c->d_amp = nullptr;
-    cudaFree(c->d_omega); c->d_omega = nullptr;
+    cudaFree(c->d_h0); c->d_h0 = nullptr;
     cudaFree(c->d_kv); c->d_kv = nullptr;
     cudaFree(c->d_tiles); c->d_tiles = nullptr;
     cudaFree(c->d_tw); c->d_tw = nullptr;
@@ -146,8 +144,7 @@ int allocate_for_size(wso_ctx* c, uint32_t n) {
     if (chunk > (size_t)wso::kMaxChunk) chunk = wso::kMaxChunk;
     if (chunk > c->max_slots) chunk = c->max_slots;
     c->chunk = (uint32_t)chunk;
-    WSO_CUDA(c, cudaMalloc(&c->d_amp, sizeof(float2) * n2 * c->max_tiles));
-    WSO_CUDA(c, cudaMalloc(&c->d_omega, sizeof(float) * n2 * c->max_tiles));
+    WSO_CUDA(c, cudaMalloc(&c->d_h0, sizeof(float4) * n2 * c->max_tiles));
     WSO_CUDA(c, cudaMalloc(&c->d_kv, sizeof(float) * n * c->max_tiles));
     WSO_CUDA(c, cudaMalloc(&c->d_tiles, sizeof(TileDev) * c->max_tiles));
     WSO_CUDA(c, cudaMalloc(&c->d_tw, sizeof(float2) * n));
@@ -172,10 +169,11 @@ int allocate_for_size(wso_ctx* c, uint32_t n) {
     WSO_CUDA(c, cudaMemcpyAsync(c->d_tw, tw.data(), sizeof(float2) * n, cudaMemcpyHostToDevice, c->stream));
     c->h_tiles.assign(c->max_tiles, TileDev{});
     for (uint32_t t = 0; t < c->max_tiles; ++t) {
-        c->h_tiles[t].amp = c->d_amp + n2 * t;
-        c->h_tiles[t].omega = c->d_omega + n2 * t;
+        c->h_tiles[t].h0 = c->d_h0 + n2 * t;
         c->h_tiles[t].kv = c->d_kv + (size_t)n * t;
         c->h_tiles[t].lambda = c->tiles[t].params.lambda;
+        c->h_tiles[t].omega0 = 0.0f;
+        c->h_tiles[t].table_len = 0;
         c->tiles[t].is_prepared = false;
         c->tiles[t].h0.clear();
     }
@@ -194,21 +192,42 @@ int upload_h0(wso_ctx* c, uint32_t tile, const wso_h0_record* h0) {
         if (!(h0[i].amp_conj_re == h0[i].amp_re && h0[i].amp_conj_im == -h0[i].amp_im))
             return fail(c, WSO_ERR_H0_NOT_CONJUGATE, "h0: heightAmp_conj != conj(heightAmp)");
     }
-    std::vector<float2> amp_t(n2);
-    std::vector<float> om_t(n2);
+    std::vector<float> kv;
+    wso::host_wave_numbers(n, c->tiles[tile].params.tile_length, kv);
+    // The quantised dispersion takes few distinct values j*omega0 (reference: QDispersion, WSTessendorf.h:284-287).
+    // When every omega is EXACTLY fl(float(j)*omega0) with a small j, the kernels use a per-frame (cos,sin) table
+    // over j instead of one sincosf per wave vector - bit-identical, since the table entry evaluates the same
+    // fp32 phase fl(omega*t).  Otherwise (e.g. an imported h0 with foreign dispersion) omega itself is stored.
+    const float omega0 = wso::derive_params(c->tiles[tile].params).base_freq;
+    int jmax = 0;
+    bool table_ok = omega0 > 0.0f;
+    for (size_t i = 0; i < n2 && table_ok; ++i) {
+        const float w = h0[i].dispersion;
+        const float jf = std::nearbyint(w / omega0);
+        if (!(jf >= 0.0f && jf < (float)wso::kMaxTable) || jf * omega0 != w) table_ok = false;
+        else if ((int)jf > jmax) jmax = (int)jf;
+    }
+    std::vector<float4> rec(n2);
     for (uint32_t m = 0; m < n; ++m)
         for (uint32_t k = 0; k < n; ++k) {
             const wso_h0_record& r = h0[(size_t)m * n + k];
-            amp_t[(size_t)k * n + m] = make_float2(r.amp_re, r.amp_im);
-            om_t[(size_t)k * n + m] = r.dispersion;
+            // 1/|k| exactly as glm::normalize computes it (reference: WSTessendorf.h:133-136)
+            const float d = kv[k] * kv[k] + kv[m] * kv[m];
+            const float inv = std::sqrt(d) > 0.00001f ? 1.0f / std::sqrt(d) : 0.0f;
+            float wfield = r.dispersion;
+            if (table_ok) {
+                const int j = (int)std::nearbyint(r.dispersion / omega0);
+                std::memcpy(&wfield, &j, sizeof(float));
+            }
+            rec[(size_t)k * n + m] = make_float4(r.amp_re, r.amp_im, inv, wfield);
         }
-    std::vector<float> kv;
-    wso::host_wave_numbers(n, c->tiles[tile].params.tile_length, kv);
     WSO_CUDA(c, cudaSetDevice(c->device));
     WSO_CUDA(c, cudaStreamSynchronize(c->stream));
-    WSO_CUDA(c, cudaMemcpy(c->d_amp + n2 * tile, amp_t.data(), sizeof(float2) * n2, cudaMemcpyHostToDevice));
-    WSO_CUDA(c, cudaMemcpy(c->d_omega + n2 * tile, om_t.data(), sizeof(float) * n2, cudaMemcpyHostToDevice));
+    WSO_CUDA(c, cudaMemcpy(c->d_h0 + n2 * tile, rec.data(), sizeof(float4) * n2, cudaMemcpyHostToDevice));
     WSO_CUDA(c, cudaMemcpy(c->d_kv + (size_t)n * tile, kv.data(), sizeof(float) * n, cudaMemcpyHostToDevice));
+    c->h_tiles[tile].omega0 = omega0;
+    c->h_tiles[tile].table_len = table_ok ? jmax + 1 : 0;
+    WSO_CUDA(c, cudaMemcpy(c->d_tiles + tile, &c->h_tiles[tile], sizeof(TileDev), cudaMemcpyHostToDevice));
     Tile& tl = c->tiles[tile];
     if (tl.h0.data() != h0) tl.h0.assign(h0, h0 + n2);
     tl.prepared = tl.params;

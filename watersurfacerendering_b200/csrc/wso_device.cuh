@@ -246,6 +246,12 @@ struct Stage {
     static constexpr int LS = LineStride<N>::value;
     static constexpr int JN = N / R;               // butterflies per line
 
+    // All shared-memory offsets below are (per-thread base) + (compile-time constant): with JN and NS*R
+    // multiples of 16 (or NS < 16 dividing 16) the padding term of element base + r*stride is
+    // pad(base) + r*stride + ((r*stride) >> 4).
+    static constexpr int kLoadStep = JN + (JN >> 4);   // pad_idx(j + r*JN) - pad_idx(j + (r-1)*JN), JN % 16 == 0
+    static constexpr bool kLoadConst = (JN % 16) == 0;
+
     static WSO_HD void load(const float2* smem, int tid, ThreadState& st) {
 #pragma unroll
         for (int i = 0; i < NB; ++i) {
@@ -253,8 +259,29 @@ struct Stage {
             const int line = u / JN;
             const int j = u % JN;
             const float2* x = smem + line * LS;
+            if (kLoadConst) {
+                const float2* xb = x + pad_idx(j);
 #pragma unroll
-            for (int r = 0; r < R; ++r) st.v[i * R + r] = x[pad_idx(j + r * JN)];
+                for (int r = 0; r < R; ++r) st.v[i * R + r] = xb[r * kLoadStep];
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; ++r) st.v[i * R + r] = x[pad_idx(j + r * JN)];
+            }
+        }
+    }
+
+    // Twiddles w^r, r = 1..R-1, from ONE table load (w = w_{NS*R}^k) and a product tree of depth <= 4
+    // (w^r = w^floor(r/2) * w^ceil(r/2)); fifteen scattered 8-byte loads per radix-16 butterfly would
+    // otherwise dominate the load/store pipe.
+    template <int RR>
+    static WSO_HD void apply_powers(float2* v, float2 w1) {
+        float2 w[RR > 1 ? RR : 2];
+        w[1] = w1;
+        v[1] = cmul(v[1], w1);
+#pragma unroll
+        for (int r = 2; r < RR; ++r) {
+            w[r] = cmul(w[r >> 1], w[(r + 1) >> 1]);
+            v[r] = cmul(v[r], w[r]);
         }
     }
 
@@ -266,11 +293,20 @@ struct Stage {
                 const int j = u % JN;
                 const int k = j % NS;
                 constexpr int tstep = N / (NS * R);
-#pragma unroll
-                for (int r = 1; r < R; ++r) st.v[i * R + r] = cmul(st.v[i * R + r], tw[tstep * k * r]);
+                apply_powers<R>(&st.v[i * R], tw[tstep * k]);
             }
             Dft<R>::run(&st.v[i * R]);
         }
+    }
+
+    // store offsets: element base + r*NS with base = (j/NS)*NS*R + k, k < NS.
+    //   NS % 16 == 0 : pad(base + r*NS) = pad(base) + r*(NS + NS/16)
+    //   NS < 16      : base % 16 == k when NS*R % 16 == 0 (or base % R == 0 with R | 16 when NS == 1), so
+    //                  pad(base + r*NS) = pad(base) + r*NS + ((r*NS) >> 4)
+    static constexpr bool kStoreConst =
+        (NS % 16 == 0) || ((NS * R) % 16 == 0 && 16 % NS == 0) || (NS == 1 && 16 % R == 0);
+    static WSO_HD constexpr int store_off(int r) {
+        return (NS % 16 == 0) ? r * (NS + (NS >> 4)) : r * NS + ((r * NS) >> 4);
     }
 
     static WSO_HD void store(float2* smem, int tid, const ThreadState& st) {
@@ -282,8 +318,14 @@ struct Stage {
             const int k = j % NS;
             const int base = (j / NS) * NS * R + k;
             float2* y = smem + line * LS;
+            if (kStoreConst) {
+                float2* yb = y + pad_idx(base);
 #pragma unroll
-            for (int r = 0; r < R; ++r) y[pad_idx(base + r * NS)] = st.v[i * R + r];
+                for (int r = 0; r < R; ++r) yb[store_off(r)] = st.v[i * R + r];
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; ++r) y[pad_idx(base + r * NS)] = st.v[i * R + r];
+            }
         }
     }
 };

@@ -19,8 +19,12 @@ template <> struct Cfg<11> { static constexpr int CP = 4, NF = 1, RI = 2; };
 template <> struct Cfg<12> { static constexpr int CP = 4, NF = 1, RI = 2; };
 template <> struct Cfg<13> { static constexpr int CP = 2, NF = 1, RI = 1; };
 
+// 1024 resident threads per SM at <= 64 registers: every thread carries 16 complex values between barriers
+constexpr int min_blocks(int threads) { return threads >= 1024 ? 1 : (1024 / threads > 8 ? 8 : 1024 / threads); }
+
 template <int LOGN>
-__global__ void __launch_bounds__(Pass1<LOGN, Cfg<LOGN>::CP, Cfg<LOGN>::NF>::T)
+__global__ void __launch_bounds__(Pass1<LOGN, Cfg<LOGN>::CP, Cfg<LOGN>::NF>::T,
+                                  min_blocks(Pass1<LOGN, Cfg<LOGN>::CP, Cfg<LOGN>::NF>::T))
 wso_pass1_kernel(const __grid_constant__ LaunchArgs args) {
     extern __shared__ __align__(16) float2 smem[];
     DeviceExec ex;
@@ -28,7 +32,7 @@ wso_pass1_kernel(const __grid_constant__ LaunchArgs args) {
 }
 
 template <int LOGN>
-__global__ void __launch_bounds__(Pass2<LOGN, Cfg<LOGN>::RI>::T)
+__global__ void __launch_bounds__(Pass2<LOGN, Cfg<LOGN>::RI>::T, min_blocks(Pass2<LOGN, Cfg<LOGN>::RI>::T))
 wso_pass2_kernel(const __grid_constant__ LaunchArgs args) {
     extern __shared__ __align__(16) float2 smem[];
     DeviceExec ex;

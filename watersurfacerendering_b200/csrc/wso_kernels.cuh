@@ -10,19 +10,27 @@
 // seven fftwf_execute calls (cpp:338-378).
 #pragma once
 
+#include <cstring>
+
 #include "wso_device.cuh"
 
 namespace wso {
 
-static constexpr int kMaxChunk = 64;  // batch items (tile-frames) per kernel launch
+static constexpr int kMaxChunk = 64;   // batch items (tile-frames) per kernel launch
+static constexpr int kMaxTable = 1024;  // entries of the per-frame sincos table kept in shared memory
 
 // Per-tile constants, device pointers (written once per Prepare()).
 struct TileDev {
-    const float2* amp;   // [n][m] (TRANSPOSED): heightAmp of wave vector (m,n); reference h0 record re,im
-    const float* omega;  // [n][m] (TRANSPOSED): quantised dispersion (reference: WSTessendorf.h:284-287)
+    // [n][m] (TRANSPOSED) one 16-byte record per wave vector (m,n):
+    //   x,y = heightAmp re,im (reference h0 record)          z = 1/|k| (0 where |k| <= 1e-5: WSTessendorf.h:135)
+    //   w   = quantised dispersion omega (WSTessendorf.h:284-287), or - when table_len > 0 - its integer
+    //         multiple j of the base frequency (omega == fl(float(j)*omega0) exactly, checked at Prepare)
+    const float4* h0;
     const float* kv;     // [N]: kv[i] = (float)(M_PI*(2.0f*i-N)/L)  (reference: WSTessendorf.cpp:75-80)
     float lambda;        // displacement scale (reference: WSTessendorf.h:181)
-    float pad_;
+    float omega0;        // base frequency (float)(2*pi/T)
+    int table_len;       // j_max+1 when the per-frame sincos table is usable, else 0
+    int pad_;
 };
 
 struct BatchItem {
@@ -53,26 +61,31 @@ struct Point {
 // h~(k,t) and the wave-vector factors for wave vector (m,n).
 // reference: WaveHeightFT, WSTessendorf.h:265-275 with heightAmp_conj == conj(heightAmp) (validated at
 // import): h~ = 2*(a*cos(wt) - b*sin(wt)), imaginary part exactly 0.  Unit vector: WSTessendorf.h:133-136.
-WSO_HD Point eval_point(const TileDev& td, int N, int m, int n, float t) {
-    const int idx = n * N + m;
-    const float2 a = td.amp[idx];
-    const float w = td.omega[idx];
+// The phase w*t is the same single fp32 product as the reference's; with TABLE the (cos,sin) pair comes
+// from the per-frame table over j (bit-identical: the table entry is sincosf(fl(fl(j*omega0)*t))).
+template <bool TABLE>
+WSO_HD Point eval_point(const TileDev& td, const float2* table, int N, int m, int n, float t) {
+    const float4 q = td.h0[n * N + m];
     float s, c;
-    sincos_acc(rmul(w, t), &s, &c);
-    const float x = rsub(rmul(a.x, c), rmul(a.y, s));
+    if (TABLE) {
+#if defined(__CUDA_ARCH__)
+        const float2 cs = table[__float_as_int(q.w)];
+#else
+        int j; std::memcpy(&j, &q.w, 4);
+        const float2 cs = table[j];
+#endif
+        c = cs.x;
+        s = cs.y;
+    } else {
+        sincos_acc(rmul(q.w, t), &s, &c);
+    }
+    const float x = rsub(rmul(q.x, c), rmul(q.y, s));
     Point p;
     p.H = radd(x, x);
     p.kx = td.kv[n];
     p.kz = td.kv[m];
-    const float d = radd(rmul(p.kx, p.kx), rmul(p.kz, p.kz));
-    if (sqrt_ieee(d) > 0.00001f) {
-        const float inv = rsqrt_ieee(d);
-        p.ux = rmul(p.kx, inv);
-        p.uz = rmul(p.kz, inv);
-    } else {
-        p.ux = 0.0f;
-        p.uz = 0.0f;
-    }
+    p.ux = rmul(p.kx, q.z);
+    p.uz = rmul(p.kz, q.z);
     return p;
 }
 
@@ -115,18 +128,18 @@ struct Pass1 {
     static constexpr int B = CP * NF;                 // FFT lines per CTA
     static constexpr int T = B * N / kValsPerThread;  // threads per CTA
     static constexpr int LS = LineStride<N>::value;
-    static constexpr int SMEM_BYTES = B * LS * (int)sizeof(float2);
+    static constexpr int SMEM_BYTES = (B * LS + kMaxTable) * (int)sizeof(float2);
     static_assert(T >= 1 && T <= 1024, "bad CTA size");
     static_assert(H % CP == 0 && 4 % NF == 0, "bad tiling");
 
-    template <int MASK>
-    static WSO_HD void evolve_item(const TileDev& td, float t, int fg, float2* smem, int cp, int mA,
-                                   int mB, int nA, int nB) {
+    template <int MASK, bool TABLE>
+    static WSO_HD void evolve_item(const TileDev& td, const float2* table, float t, int fg, float2* smem,
+                                   int cp, int mA, int mB, int nA, int nB) {
         Point pt[4];
-        pt[0] = eval_point(td, N, mA, nA, t);
-        pt[1] = eval_point(td, N, mA, nB, t);
-        pt[2] = eval_point(td, N, mB, nA, t);
-        pt[3] = eval_point(td, N, mB, nB, t);
+        pt[0] = eval_point<TABLE>(td, table, N, mA, nA, t);
+        pt[1] = eval_point<TABLE>(td, table, N, mA, nB, t);
+        pt[2] = eval_point<TABLE>(td, table, N, mB, nA, t);
+        pt[3] = eval_point<TABLE>(td, table, N, mB, nB, t);
         const int eA = pad_idx(mA), eB = pad_idx(mB);
         float2 a, b;
         if (NF == 4) {
@@ -169,6 +182,20 @@ struct Pass1 {
             });
         }
 
+        // ---- per-frame (cos,sin)(omega_j * t) table: omega takes few distinct values j*omega0 ------
+        float2* table = smem + B * LS;
+        const bool use_table = td.table_len > 0;
+        if (use_table) {
+            ex.each([&](int tid, ThreadState&) {
+                for (int j = tid; j < td.table_len; j += T) {
+                    float s, c;
+                    sincos_acc(rmul(rmul((float)j, td.omega0), t), &s, &c);
+                    table[j] = make_float2(c, s);
+                }
+            });
+            ex.sync();
+        }
+
         // ---- evolve: 4 points per work item (rows mA,mB x columns nA,nB), all NF fields ----------
         ex.each([&](int tid, ThreadState&) {
             for (int it = tid; it < CP * H; it += T) {
@@ -178,10 +205,17 @@ struct Pass1 {
                 const int mA = i, mB = (i == 0) ? H : N - i;
                 const int nA = j, nB = (j == 0) ? H : N - j;
                 const int mask = ((i != 0) ? 2 : 0) | ((j != 0) ? 1 : 0);
-                if (mask == 3) evolve_item<3>(td, t, by, smem, cp, mA, mB, nA, nB);
-                else if (mask == 2) evolve_item<2>(td, t, by, smem, cp, mA, mB, nA, nB);
-                else if (mask == 1) evolve_item<1>(td, t, by, smem, cp, mA, mB, nA, nB);
-                else evolve_item<0>(td, t, by, smem, cp, mA, mB, nA, nB);
+                if (use_table) {
+                    if (mask == 3) evolve_item<3, true>(td, table, t, by, smem, cp, mA, mB, nA, nB);
+                    else if (mask == 2) evolve_item<2, true>(td, table, t, by, smem, cp, mA, mB, nA, nB);
+                    else if (mask == 1) evolve_item<1, true>(td, table, t, by, smem, cp, mA, mB, nA, nB);
+                    else evolve_item<0, true>(td, table, t, by, smem, cp, mA, mB, nA, nB);
+                } else {
+                    if (mask == 3) evolve_item<3, false>(td, table, t, by, smem, cp, mA, mB, nA, nB);
+                    else if (mask == 2) evolve_item<2, false>(td, table, t, by, smem, cp, mA, mB, nA, nB);
+                    else if (mask == 1) evolve_item<1, false>(td, table, t, by, smem, cp, mA, mB, nA, nB);
+                    else evolve_item<0, false>(td, table, t, by, smem, cp, mA, mB, nA, nB);
+                }
             }
         });
         ex.sync();
