@@ -192,6 +192,23 @@ struct DeviceExec {
     }
     __device__ __forceinline__ void sync() { __syncthreads(); }
 
+    // Barrier over the G consecutive threads [g*G, (g+1)*G) that share one FFT line (or line pair), instead of
+    // the whole CTA: lines are independent between the evolve / split / pack phases, so a CTA-wide barrier per
+    // stage would only make 16 warps wait for the slowest one.  G <= 32: the group lives inside one warp;
+    // otherwise a named barrier (ids 1..15; id 0 is __syncthreads).
+    template <int G, int T>
+    __device__ __forceinline__ void sync_group(int id_base) {
+        if constexpr (G >= T) {
+            __syncthreads();
+        } else if constexpr (G <= 32) {
+            __syncwarp();
+        } else {
+            static_assert(G % 32 == 0, "group must be whole warps");
+            const int id = id_base + (int)threadIdx.x / G;
+            asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(G) : "memory");
+        }
+    }
+
     // Fold the (min,max) every thread left in st.v[0] into out[0] (min) / out[1] (max):
     // warp-shuffle butterfly, then one pair of atomics per warp.  Float ordering through the
     // sign-aware int/uint trick, valid for any mix of signs.
@@ -223,6 +240,8 @@ struct HostExec {
         for (int t = 0; t < nthreads; ++t) f(t, states[t]);
     }
     void sync() {}
+    template <int G, int T>
+    void sync_group(int) {}
     void commit_minmax(float* out) {
         for (int t = 0; t < nthreads; ++t) {
             if (states[t].v[0].x < out[0]) out[0] = states[t].v[0].x;
@@ -233,7 +252,8 @@ struct HostExec {
 
 // ---------------------------------------------------------------------------------------------
 // One Stockham stage over B lines of length N held in shared memory (in place: all loads, barrier,
-// butterflies + stores, barrier).  CTA size T = B*N/16; every thread carries 16 values.
+// butterflies + stores, barrier).  CTA size T = B*N/16; every thread carries 16 values; the N/16 threads
+// [line*G, (line+1)*G) own one line, so the barriers are per line (sync_group).
 //   radix R, NS = product of the radices of the earlier stages.
 //   load : v[r] = x[j + r*N/R]                         (unit stride across threads)
 //   twid : v[r] *= w_{NS*R}^{(j % NS) * r}
@@ -242,7 +262,8 @@ struct HostExec {
 template <int N, int B, int R, int NS>
 struct Stage {
     static constexpr int T = B * N / kValsPerThread;
-    static constexpr int NB = kValsPerThread / R;  // butterflies per thread
+    static constexpr int G = N / kValsPerThread;   // threads that share one line: tid/G = line, tid%G = lane in line
+    static constexpr int NB = kValsPerThread / R;  // butterflies per thread: j = tid%G + G*i
     static constexpr int LS = LineStride<N>::value;
     static constexpr int JN = N / R;               // butterflies per line
 
@@ -255,9 +276,8 @@ struct Stage {
     static WSO_HD void load(const float2* smem, int tid, ThreadState& st) {
 #pragma unroll
         for (int i = 0; i < NB; ++i) {
-            const int u = tid + T * i;
-            const int line = u / JN;
-            const int j = u % JN;
+            const int line = tid / G;
+            const int j = tid % G + G * i;
             const float2* x = smem + line * LS;
             if (kLoadConst) {
                 const float2* xb = x + pad_idx(j);
@@ -289,8 +309,7 @@ struct Stage {
 #pragma unroll
         for (int i = 0; i < NB; ++i) {
             if (NS > 1) {
-                const int u = tid + T * i;
-                const int j = u % JN;
+                const int j = tid % G + G * i;
                 const int k = j % NS;
                 constexpr int tstep = N / (NS * R);
                 apply_powers<R>(&st.v[i * R], tw[tstep * k]);
@@ -312,9 +331,8 @@ struct Stage {
     static WSO_HD void store(float2* smem, int tid, const ThreadState& st) {
 #pragma unroll
         for (int i = 0; i < NB; ++i) {
-            const int u = tid + T * i;
-            const int line = u / JN;
-            const int j = u % JN;
+            const int line = tid / G;
+            const int j = tid % G + G * i;
             const int k = j % NS;
             const int base = (j / NS) * NS * R + k;
             float2* y = smem + line * LS;
@@ -337,13 +355,14 @@ struct RunStages {
         constexpr int N = 1 << LOGN;
         constexpr int R = Plan<LOGN>::R[SI];
         using St = Stage<N, B, R, NS>;
+        // only the threads of one line have to agree on that line's loads and stores
         ex.each([&](int tid, ThreadState& st) { St::load(smem, tid, st); });
-        ex.sync();
+        ex.template sync_group<St::G, St::T>(1);
         ex.each([&](int tid, ThreadState& st) {
             St::twiddle_dft(tw, tid, st);
             St::store(smem, tid, st);
         });
-        ex.sync();
+        ex.template sync_group<St::G, St::T>(1);
         if constexpr (SI + 1 < Plan<LOGN>::S) RunStages<LOGN, B, SI + 1, NS * R, Exec>::run(ex, smem, tw);
     }
 };

@@ -222,6 +222,7 @@ struct Pass1 {
 
         // ---- B complex FFTs of length N along m ---------------------------------------------------
         RunStages<LOGN, B, 0, 1, Exec>::run(ex, smem, args.tw);
+        ex.sync();  // the split below reads CP lines per work item
 
         // ---- split the two real columns, keep m' in [0, N/2), store W[m'][f][slot] ---------------
         float2* Wit = args.W + (size_t)bz * ((size_t)H * 4 * N);
@@ -284,9 +285,8 @@ struct Pass2 {
             ex.each([&](int tid, ThreadState& st) {
 #pragma unroll
                 for (int i = 0; i < St::NB; ++i) {
-                    const int u = tid + T * i;
-                    const int line = u / St::JN;
-                    const int j = u % St::JN;
+                    const int line = tid / St::G;
+                    const int j = tid % St::G + St::G * i;
                     const int mp = bx * RI + (line >> 1);
                     const int f = by * 2 + (line & 1);
                     const float2* src = Wit + ((size_t)mp * 4 + f) * N;
@@ -296,17 +296,19 @@ struct Pass2 {
                 St::twiddle_dft(args.tw, tid, st);
                 St::store(smem, tid, st);
             });
-            ex.sync();
+            ex.template sync_group<St::G, T>(1);
             if constexpr (Plan<LOGN>::S > 1) RunStages<LOGN, B, 1, R, Exec>::run(ex, smem, args.tw);
         }
+        // the pack phase of a row item reads both of its lines: barrier over that pair of line groups
+        constexpr int G2 = 2 * (N / kValsPerThread);
+        ex.template sync_group<G2, T>(1 + ((N / kValsPerThread) > 32 ? B : 0));
 
         // ---- pack: each transformed line pair yields output rows m' and N-m' ---------------------
         float4* out = (by == 0 ? args.disp : args.norm) + (size_t)item.slot * ((size_t)N * N);
         ex.each([&](int tid, ThreadState& st) {
             float mn = kInitMin, mx = kInitMax;
-            for (int it = tid; it < RI * N; it += T) {
-                const int ri = it / N;
-                const int c = it % N;                 // output column n'
+            const int ri = tid / G2;                  // the row item this thread's line pair belongs to
+            for (int c = tid % G2; c < N; c += G2) {  // output column n'
                 const int cm = (N - c) & (N - 1);     // mirrored column
                 const int mp = bx * RI + ri;
                 const float2* l0 = smem + (ri * 2 + 0) * LS;
