@@ -3,7 +3,7 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c3|c4]
 
-A "step" = one batch of tile-frames through ComputeWaves (K1 evolve+transform, K2 transform+pack, K3 normalise).
+A "step" = one batch of tile-frames through ComputeWaves (K1 evolve+transform, K2h height extrema, K2 transform+pack).
 Default workload = BASELINE.json configs[1]: 1024x1024 tile, animation frames t_i = i*0.05 s (1000 frames =
 10 steps x 100 frames).  Under torchrun every rank owns one GPU and processes its own frames (frames are
 independent: weak scaling, no data-path collective); the timed region is bracketed by barrier + synchronize and
@@ -29,11 +29,13 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# algorithmic bytes per grid point per tile-frame of THIS design: K1 reads h0 (amp 8 + omega 4)
-# and writes the Hermitian-packed intermediate (4 fields x 4 B); K2 reads it and writes both RGBA32F maps;
-# K3 reads+writes disp.y.  (SURVEY.md §8d's two-pass model of a 7-field C2R design is 40 / 60 / 8 = 108.)
-BYTES_PER_POINT = {"K1": 28.0, "K2": 48.0, "K3": 8.0}
-SURVEY_BYTES_PER_POINT = {"K1": 40.0, "K2": 60.0, "K3": 8.0}
+# algorithmic bytes per grid point per tile-frame of THIS design: K1 reads the 16-byte h0 record
+# and writes the Hermitian-packed intermediate W (4 packed fields x 4 B); K2h re-reads packed field 0 (4 B) for the
+# height extrema; K2 reads W and writes both RGBA32F maps (disp.y already normalised - no second pass).
+# (SURVEY.md §8d's two-pass model of a 7-field C2R design is 40 / 8 / 60 = 108.)
+KERNELS = ["K1", "K2h", "K2"]
+BYTES_PER_POINT = {"K1": 32.0, "K2h": 4.0, "K2": 48.0}
+SURVEY_BYTES_PER_POINT = {"K1": 40.0, "K2h": 8.0, "K2": 60.0}
 
 WORKLOADS = {
     # name: (N, tile_length, seed, frames per step, tiles, description)
@@ -305,7 +307,7 @@ def main():
     run_steps(args.warmup, args.steps)
     prof = ws.profile()
     ws.set_profiling(False)
-    names = ["K1", "K2", "K3"]
+    names = KERNELS
     kms = prof["ms"]
     dom = int(np.argmax(kms))
     peak, peak_src = measured_peak()
@@ -324,8 +326,8 @@ def main():
     achieved = gbs(BYTES_PER_POINT[names[dom]], dom)
     roofline = {
         "bound": "hbm", "kernel": {"K1": "wso_pass1_kernel (evolve + first transform)",
-                                   "K2": "wso_pass2_kernel (second transform + pack)",
-                                   "K3": "wso_normalize_kernel"}[names[dom]],
+                                   "K2h": "wso_heights_kernel (height extrema)",
+                                   "K2": "wso_pass2_kernel (second transform + pack)"}[names[dom]],
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
         "peak_source": peak_src, "traffic": traffic,
         "algorithmic_bytes_per_launch": BYTES_PER_POINT[names[dom]] * pts * prof["tile_frames"] / max(prof["launches"], 1),

@@ -138,7 +138,7 @@ WSO_API int wso_get_stats(const wso_ctx* ctx, uint64_t* kernel_launches, uint32_
 /* Opt-in per-kernel device timing (the analogue of the reference's VKP_PROFILE_SCOPE table,
  * core/Profile.h:16-32): with profiling on, every launch is bracketed by CUDA events on the compute
  * stream.  wso_get_profile synchronises and returns the accumulated milliseconds of
- * {K1 evolve+first transform, K2 second transform+pack, K3 normalise}, the number of launches of each
+ * {K1 evolve+first transform, K2h height extrema, K2 second transform+pack}, the number of launches of each
  * and the tile-frames they covered since wso_set_profiling(ctx, 1). */
 WSO_API int wso_set_profiling(wso_ctx* ctx, int on);
 WSO_API int wso_get_profile(wso_ctx* ctx, double* kernel_ms3, uint64_t* launches, uint64_t* tile_frames);

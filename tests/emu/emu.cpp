@@ -16,7 +16,8 @@ static int run_cfg(const float* amp_t, const float* omega_t, const float* kv, fl
                    float t, float* disp, float* norm, float* minmax, float* amp_out, float* w_out) {
     constexpr int N = 1 << LOGN, H = N / 2;
     using P1 = Pass1<LOGN, CP, NF>;
-    using P2 = Pass2<LOGN, RI>;
+    using P2 = Pass2<LOGN, RI, false>;
+    using PH = Pass2<LOGN, RI, true>;
     std::vector<float2> tw(N);
     for (int k = 0; k < N; ++k) {
         const double a = 2.0 * 3.14159265358979323846 * k / N;
@@ -74,6 +75,15 @@ static int run_cfg(const float* amp_t, const float* omega_t, const float* kv, fl
             }
     }
     if (w_out) std::memcpy(w_out, W.data(), W.size() * sizeof(float2));
+    {   // K2h: height extrema
+        std::vector<float2> smem(PH::SMEM_BYTES / sizeof(float2));
+        std::vector<ThreadState> st(PH::T);
+        for (int bx = 0; bx < H / RI; ++bx) {
+            for (auto& v : smem) v = make_float2(NAN, NAN);
+            HostExec ex{PH::T, st.data()};
+            PH::run(ex, smem.data(), bx, 0, 0, args);
+        }
+    }
     {
         std::vector<float2> smem(P2::SMEM_BYTES / sizeof(float2));
         std::vector<ThreadState> st(P2::T);
@@ -84,10 +94,6 @@ static int run_cfg(const float* amp_t, const float* omega_t, const float* kv, fl
                 P2::run(ex, smem.data(), bx, by, 0, args);
             }
     }
-    const float a = amplitude_of(minmax[0], minmax[1]);
-    const float inv = 1.0f / a;
-    for (size_t i = 0; i < (size_t)N * N; ++i) disp[4 * i + 1] *= inv;
-    *amp_out = a;
     return 0;
 }
 

@@ -34,6 +34,7 @@ namespace wso {
 WSO_HD float rmul(float a, float b) { return __fmul_rn(a, b); }
 WSO_HD float radd(float a, float b) { return __fadd_rn(a, b); }
 WSO_HD float rsub(float a, float b) { return __fsub_rn(a, b); }
+WSO_HD float rdiv(float a, float b) { return __fdiv_rn(a, b); }
 WSO_HD float rsqrt_ieee(float a) { return __fdiv_rn(1.0f, __fsqrt_rn(a)); }
 WSO_HD float sqrt_ieee(float a) { return __fsqrt_rn(a); }
 WSO_HD void sincos_acc(float x, float* s, float* c) { sincosf(x, s, c); }
@@ -41,6 +42,7 @@ WSO_HD void sincos_acc(float x, float* s, float* c) { sincosf(x, s, c); }
 WSO_HD float rmul(float a, float b) { return a * b; }
 WSO_HD float radd(float a, float b) { return a + b; }
 WSO_HD float rsub(float a, float b) { return a - b; }
+WSO_HD float rdiv(float a, float b) { return a / b; }
 WSO_HD float rsqrt_ieee(float a) { return 1.0f / std::sqrt(a); }
 WSO_HD float sqrt_ieee(float a) { return std::sqrt(a); }
 WSO_HD void sincos_acc(float x, float* s, float* c) {

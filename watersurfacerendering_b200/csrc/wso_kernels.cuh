@@ -58,20 +58,20 @@ struct Point {
     float H, kx, kz, ux, uz;
 };
 
-// h~(k,t) and the wave-vector factors for wave vector (m,n).
+// h~(k,t) for the wave vector whose 16-byte record is q.
 // reference: WaveHeightFT, WSTessendorf.h:265-275 with heightAmp_conj == conj(heightAmp) (validated at
-// import): h~ = 2*(a*cos(wt) - b*sin(wt)), imaginary part exactly 0.  Unit vector: WSTessendorf.h:133-136.
+// import): h~ = 2*(a*cos(wt) - b*sin(wt)), imaginary part exactly 0.
 // The phase w*t is the same single fp32 product as the reference's; with TABLE the (cos,sin) pair comes
 // from the per-frame table over j (bit-identical: the table entry is sincosf(fl(fl(j*omega0)*t))).
 template <bool TABLE>
-WSO_HD Point eval_point(const TileDev& td, const float2* table, int N, int m, int n, float t) {
-    const float4 q = td.h0[n * N + m];
+WSO_HD float eval_height(const float4 q, const float2* table, float t) {
     float s, c;
     if (TABLE) {
 #if defined(__CUDA_ARCH__)
         const float2 cs = table[__float_as_int(q.w)];
 #else
-        int j; std::memcpy(&j, &q.w, 4);
+        int j;
+        std::memcpy(&j, &q.w, 4);
         const float2 cs = table[j];
 #endif
         c = cs.x;
@@ -80,18 +80,12 @@ WSO_HD Point eval_point(const TileDev& td, const float2* table, int N, int m, in
         sincos_acc(rmul(q.w, t), &s, &c);
     }
     const float x = rsub(rmul(q.x, c), rmul(q.y, s));
-    Point p;
-    p.H = radd(x, x);
-    p.kx = td.kv[n];
-    p.kz = td.kv[m];
-    p.ux = rmul(p.kx, q.z);
-    p.uz = rmul(p.kz, q.z);
-    return p;
+    return radd(x, x);
 }
 
 // Even-type (real spectrum) and odd-type (imaginary spectrum i*V) member of packed field F.
 //   F=0: (height, Dx)   F=1: (none, Dz)   F=2: (dxDx, slopeX)   F=3: (dzDz, slopeZ)
-// reference: WSTessendorf.cpp:303-336 (same products in the same order).
+// reference: WSTessendorf.cpp:303-336 (same products in the same order).  ux,uz: WSTessendorf.h:133-136.
 template <int F>
 WSO_HD void field_values(const Point& p, float* R, float* V) {
     if (F == 0) { *R = p.H;                              *V = rmul(-p.ux, p.H); }
@@ -100,22 +94,51 @@ WSO_HD void field_values(const Point& p, float* R, float* V) {
     if (F == 3) { *R = rmul(p.kz, rmul(p.uz, p.H));      *V = rmul(p.kz, p.H); }
 }
 
-// Z = even(R) - odd(V) under DFT-index reflection, for the 4 points (mA|mB) x (nA|nB).
-// MASK bit1: rows are mirrored into each other (i >= 1); bit0: columns are (j >= 1).
-template <int F, int MASK>
-WSO_HD void pack_field(const Point (&pt)[4], float2* outA, float2* outB) {
+// GENERAL packing (any mirror pattern): Z = even(R) - odd(V) under DFT-index reflection, for the 4 points
+// q = 2*a + b, a = row (mA,mB), b = column (nA,nB).  MASK bit1: the rows mirror into each other (i >= 1);
+// bit0: the columns do (j >= 1).  Used on the index-0 (Nyquist) and N/2 (DC) lines, where the mirror of
+// a point keeps one of its wave numbers; everywhere else pack_interior applies.
+template <int F>
+WSO_HD void pack_general(const Point (&pt)[4], int mask, float2* outA, float2* outB) {
     float R[4], V[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) field_values<F>(pt[q], &R[q], &V[q]);
     float z[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        const int qm = q ^ MASK;
-        z[q] = 0.5f * (R[q] + R[qm]) - 0.5f * (V[q] - V[qm]);
+        // mirror partner q ^ mask, selected without dynamic register indexing
+        const float Rm = (mask == 3) ? R[q ^ 3] : (mask == 2) ? R[q ^ 2] : (mask == 1) ? R[q ^ 1] : R[q];
+        const float Vm = (mask == 3) ? V[q ^ 3] : (mask == 2) ? V[q ^ 2] : (mask == 1) ? V[q ^ 1] : V[q];
+        z[q] = 0.5f * (R[q] + Rm) - 0.5f * (V[q] - Vm);
     }
-    // q = 2*a + b : a = row (A,B), b = column (A,B).  complex sample = Z(m, nA) + i Z(m, nB)
-    *outA = make_float2(z[0], z[1]);
+    *outA = make_float2(z[0], z[1]);  // complex sample of row mA: Z(mA,nA) + i Z(mA,nB)
     *outB = make_float2(z[2], z[3]);
+}
+
+// INTERIOR packing (i >= 1 and j >= 1): the mirror of (m,n) is (N-m,N-n) with BOTH wave numbers negated, so
+// every packed field depends on h~ only through S = h~(k) + h~(-k):
+//   F0: Z(k) = S/2 * (1 + ux)      F1: Z(k) = S/2 * uz      F2: Z(k) = S/2 * kx*(ux - 1)     F3: same with z
+// and Z(-k) follows by ux -> -ux, kx -> -kx.  s0 = S(mA,nA)/2, s1 = S(mA,nB)/2; (kx,kz,inv) of those two points.
+template <int F>
+WSO_HD void pack_interior(float s0, float kx0, float kz0, float inv0, float s1, float kx1, float kz1, float inv1,
+                          float2* outA, float2* outB) {
+    float z0, z1, z2, z3;
+    if (F == 0) {
+        const float a = kx0 * inv0 * s0, b = kx1 * inv1 * s1;
+        z0 = s0 + a; z3 = s0 - a; z1 = s1 + b; z2 = s1 - b;
+    } else if (F == 1) {
+        z0 = kz0 * inv0 * s0; z3 = -z0; z1 = kz1 * inv1 * s1; z2 = -z1;
+    } else if (F == 2) {
+        const float g0 = kx0 * s0, g1 = kx1 * s1;
+        const float a = kx0 * inv0 * g0, b = kx1 * inv1 * g1;
+        z0 = a - g0; z3 = a + g0; z1 = b - g1; z2 = b + g1;
+    } else {
+        const float g0 = kz0 * s0, g1 = kz1 * s1;
+        const float a = kz0 * inv0 * g0, b = kz1 * inv1 * g1;
+        z0 = a - g0; z3 = a + g0; z1 = b - g1; z2 = b + g1;
+    }
+    *outA = make_float2(z0, z1);
+    *outB = make_float2(z2, z3);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -131,37 +154,72 @@ struct Pass1 {
     static constexpr int SMEM_BYTES = (B * LS + kMaxTable) * (int)sizeof(float2);
     static_assert(T >= 1 && T <= 1024, "bad CTA size");
     static_assert(H % CP == 0 && 4 % NF == 0, "bad tiling");
+    // evolve work split: IT threads walk the row pairs i, CG thread groups walk the column pairs
+    static constexpr int IT = (T < H) ? T : H;
+    static constexpr int CG = T / IT;
+    static_assert(T % IT == 0 && (CG <= CP), "bad evolve split");
 
-    template <int MASK, bool TABLE>
+    template <int F>
+    static WSO_HD void put(float2* smem, int fl, int cp, int eA, int eB, float2 a, float2 b) {
+        (void)F;
+        smem[(fl * CP + cp) * LS + eA] = a;
+        smem[(fl * CP + cp) * LS + eB] = b;
+    }
+
+    // one work item = rows (mA,mB) x columns (nA,nB): 4 wave vectors, NF packed fields each
+    template <bool TABLE>
     static WSO_HD void evolve_item(const TileDev& td, const float2* table, float t, int fg, float2* smem,
-                                   int cp, int mA, int mB, int nA, int nB) {
-        Point pt[4];
-        pt[0] = eval_point<TABLE>(td, table, N, mA, nA, t);
-        pt[1] = eval_point<TABLE>(td, table, N, mA, nB, t);
-        pt[2] = eval_point<TABLE>(td, table, N, mB, nA, t);
-        pt[3] = eval_point<TABLE>(td, table, N, mB, nB, t);
+                                   int cp, int i, int j) {
+        const int mA = i, mB = (i == 0) ? H : N - i;
+        const int nA = j, nB = (j == 0) ? H : N - j;
+        const float4 q0 = td.h0[nA * N + mA], q1 = td.h0[nB * N + mA];
+        const float4 q2 = td.h0[nA * N + mB], q3 = td.h0[nB * N + mB];
+        const float h0 = eval_height<TABLE>(q0, table, t), h1 = eval_height<TABLE>(q1, table, t);
+        const float h2 = eval_height<TABLE>(q2, table, t), h3 = eval_height<TABLE>(q3, table, t);
+        const float kxA = td.kv[nA], kxB = td.kv[nB], kzA = td.kv[mA], kzB = td.kv[mB];
         const int eA = pad_idx(mA), eB = pad_idx(mB);
         float2 a, b;
-        if (NF == 4) {
-            pack_field<0, MASK>(pt, &a, &b); smem[(0 * CP + cp) * LS + eA] = a; smem[(0 * CP + cp) * LS + eB] = b;
-            pack_field<1, MASK>(pt, &a, &b); smem[(1 * CP + cp) * LS + eA] = a; smem[(1 * CP + cp) * LS + eB] = b;
-            pack_field<2, MASK>(pt, &a, &b); smem[(2 * CP + cp) * LS + eA] = a; smem[(2 * CP + cp) * LS + eB] = b;
-            pack_field<3, MASK>(pt, &a, &b); smem[(3 * CP + cp) * LS + eA] = a; smem[(3 * CP + cp) * LS + eB] = b;
-        } else if (NF == 2) {
-            if (fg == 0) {
-                pack_field<0, MASK>(pt, &a, &b); smem[(0 * CP + cp) * LS + eA] = a; smem[(0 * CP + cp) * LS + eB] = b;
-                pack_field<1, MASK>(pt, &a, &b); smem[(1 * CP + cp) * LS + eA] = a; smem[(1 * CP + cp) * LS + eB] = b;
-            } else {
-                pack_field<2, MASK>(pt, &a, &b); smem[(0 * CP + cp) * LS + eA] = a; smem[(0 * CP + cp) * LS + eB] = b;
-                pack_field<3, MASK>(pt, &a, &b); smem[(1 * CP + cp) * LS + eA] = a; smem[(1 * CP + cp) * LS + eB] = b;
+        if (i != 0 && j != 0) {
+            const float s0 = 0.5f * (h0 + h3), s1 = 0.5f * (h1 + h2);
+            if (NF == 4 || (NF == 2 && fg == 0) || (NF == 1 && fg == 0)) {
+                pack_interior<0>(s0, kxA, kzA, q0.z, s1, kxB, kzA, q1.z, &a, &b);
+                put<0>(smem, 0, cp, eA, eB, a, b);
+            }
+            if (NF == 4 || (NF == 2 && fg == 0) || (NF == 1 && fg == 1)) {
+                pack_interior<1>(s0, kxA, kzA, q0.z, s1, kxB, kzA, q1.z, &a, &b);
+                put<1>(smem, NF == 1 ? 0 : 1, cp, eA, eB, a, b);
+            }
+            if (NF == 4 || (NF == 2 && fg == 1) || (NF == 1 && fg == 2)) {
+                pack_interior<2>(s0, kxA, kzA, q0.z, s1, kxB, kzA, q1.z, &a, &b);
+                put<2>(smem, NF == 4 ? 2 : 0, cp, eA, eB, a, b);
+            }
+            if (NF == 4 || (NF == 2 && fg == 1) || (NF == 1 && fg == 3)) {
+                pack_interior<3>(s0, kxA, kzA, q0.z, s1, kxB, kzA, q1.z, &a, &b);
+                put<3>(smem, NF == 4 ? 3 : (NF == 2 ? 1 : 0), cp, eA, eB, a, b);
             }
         } else {
-            if (fg == 0) pack_field<0, MASK>(pt, &a, &b);
-            if (fg == 1) pack_field<1, MASK>(pt, &a, &b);
-            if (fg == 2) pack_field<2, MASK>(pt, &a, &b);
-            if (fg == 3) pack_field<3, MASK>(pt, &a, &b);
-            smem[cp * LS + eA] = a;
-            smem[cp * LS + eB] = b;
+            const int mask = ((i != 0) ? 2 : 0) | ((j != 0) ? 1 : 0);
+            Point pt[4];
+            pt[0] = Point{h0, kxA, kzA, rmul(kxA, q0.z), rmul(kzA, q0.z)};
+            pt[1] = Point{h1, kxB, kzA, rmul(kxB, q1.z), rmul(kzA, q1.z)};
+            pt[2] = Point{h2, kxA, kzB, rmul(kxA, q2.z), rmul(kzB, q2.z)};
+            pt[3] = Point{h3, kxB, kzB, rmul(kxB, q3.z), rmul(kzB, q3.z)};
+            if (NF == 4 || (NF == 2 && fg == 0) || (NF == 1 && fg == 0)) {
+                pack_general<0>(pt, mask, &a, &b);
+                put<0>(smem, 0, cp, eA, eB, a, b);
+            }
+            if (NF == 4 || (NF == 2 && fg == 0) || (NF == 1 && fg == 1)) {
+                pack_general<1>(pt, mask, &a, &b);
+                put<1>(smem, NF == 1 ? 0 : 1, cp, eA, eB, a, b);
+            }
+            if (NF == 4 || (NF == 2 && fg == 1) || (NF == 1 && fg == 2)) {
+                pack_general<2>(pt, mask, &a, &b);
+                put<2>(smem, NF == 4 ? 2 : 0, cp, eA, eB, a, b);
+            }
+            if (NF == 4 || (NF == 2 && fg == 1) || (NF == 1 && fg == 3)) {
+                pack_general<3>(pt, mask, &a, &b);
+                put<3>(smem, NF == 4 ? 3 : (NF == 2 ? 1 : 0), cp, eA, eB, a, b);
+            }
         }
     }
 
@@ -196,27 +254,14 @@ struct Pass1 {
             ex.sync();
         }
 
-        // ---- evolve: 4 points per work item (rows mA,mB x columns nA,nB), all NF fields ----------
+        // ---- evolve: 4 wave vectors per work item, all NF fields ------------------------------------
         ex.each([&](int tid, ThreadState&) {
-            for (int it = tid; it < CP * H; it += T) {
-                const int cp = it / H;
-                const int i = it % H;
-                const int j = bx * CP + cp;
-                const int mA = i, mB = (i == 0) ? H : N - i;
-                const int nA = j, nB = (j == 0) ? H : N - j;
-                const int mask = ((i != 0) ? 2 : 0) | ((j != 0) ? 1 : 0);
-                if (use_table) {
-                    if (mask == 3) evolve_item<3, true>(td, table, t, by, smem, cp, mA, mB, nA, nB);
-                    else if (mask == 2) evolve_item<2, true>(td, table, t, by, smem, cp, mA, mB, nA, nB);
-                    else if (mask == 1) evolve_item<1, true>(td, table, t, by, smem, cp, mA, mB, nA, nB);
-                    else evolve_item<0, true>(td, table, t, by, smem, cp, mA, mB, nA, nB);
-                } else {
-                    if (mask == 3) evolve_item<3, false>(td, table, t, by, smem, cp, mA, mB, nA, nB);
-                    else if (mask == 2) evolve_item<2, false>(td, table, t, by, smem, cp, mA, mB, nA, nB);
-                    else if (mask == 1) evolve_item<1, false>(td, table, t, by, smem, cp, mA, mB, nA, nB);
-                    else evolve_item<0, false>(td, table, t, by, smem, cp, mA, mB, nA, nB);
+            const int i0 = tid % IT, cg = tid / IT;
+            for (int i = i0; i < H; i += IT)
+                for (int cp = cg; cp < CP; cp += CG) {
+                    if (use_table) evolve_item<true>(td, table, t, by, smem, cp, i, bx * CP + cp);
+                    else evolve_item<false>(td, table, t, by, smem, cp, i, bx * CP + cp);
                 }
-            }
         });
         ex.sync();
 
@@ -225,11 +270,13 @@ struct Pass1 {
         ex.sync();  // the split below reads CP lines per work item
 
         // ---- split the two real columns, keep m' in [0, N/2), store W[m'][f][slot] ---------------
+        // thread -> fixed column pair cp = tid % CP (CP adjacent slots = one 8*CP-byte segment per m'),
+        // and (field, m') pairs rest = tid/CP + k*(T/CP)
         float2* Wit = args.W + (size_t)bz * ((size_t)H * 4 * N);
         ex.each([&](int tid, ThreadState&) {
-            for (int it = tid; it < NF * H * CP; it += T) {
-                const int cp = it % CP;
-                const int rest = it / CP;
+            const int cp = tid % CP;
+            const int j = bx * CP + cp;
+            for (int rest = tid / CP; rest < NF * H; rest += T / CP) {
                 const int mp = rest % H;
                 const int fl = rest / H;
                 const float2* line = smem + (fl * CP + cp) * LS;
@@ -242,40 +289,50 @@ struct Pass1 {
                     wa.y = ch.x;
                     wb.y = ch.y;
                 }
-                const int f = by * NF + fl;
-                const int j = bx * CP + cp;
-                float2* dst = Wit + ((size_t)mp * 4 + f) * N;
-                dst[j] = wa;
-                dst[H + j] = wb;
+                float2* dst = Wit + ((size_t)mp * 4 + (by * NF + fl)) * N + j;
+                dst[0] = wa;
+                dst[H] = wb;
             }
         });
     }
 };
 
 // -------------------------------------------------------------------------------------------------
-// K2
+// K2 (maps) and K2h (height extrema only)
 // -------------------------------------------------------------------------------------------------
 WSO_HD int slot_of_column(int n, int N) {
     const int H = N >> 1;
     return (n < H) ? n : ((n == H) ? H : H + (N - n));
 }
 
-template <int LOGN, int RI>
+// reference: NormalizeHeights, WSTessendorf.cpp:443-455
+WSO_HD float amplitude_of(float mn, float mx) {
+    const float a = mn < 0.0f ? -mn : mn;
+    const float b = mx < 0.0f ? -mx : mx;
+    return a > b ? a : b;
+}
+
+// HEIGHT_ONLY = true : K2h - transforms only packed field 0 of every row item and reduces min/max of the height
+//                      (A = max(|min|,|max|) must be known before any disp.y can be written normalised).
+// HEIGHT_ONLY = false: K2  - all four fields; by = 0 writes the displacement map (fields 0,1; disp.y already
+//                      multiplied by 1/A), by = 1 the normal map (fields 2,3).
+template <int LOGN, int RI, bool HEIGHT_ONLY>
 struct Pass2 {
     static constexpr int N = 1 << LOGN;
     static constexpr int H = N / 2;
-    static constexpr int B = RI * 2;
+    static constexpr int LPI = HEIGHT_ONLY ? 1 : 2;  // lines per row item
+    static constexpr int B = RI * LPI;
     static constexpr int T = B * N / kValsPerThread;
+    static constexpr int G = N / kValsPerThread;     // threads per line
+    static constexpr int GI = LPI * G;               // threads per row item
     static constexpr int LS = LineStride<N>::value;
     static constexpr int SMEM_BYTES = B * LS * (int)sizeof(float2);
     static_assert(T >= 1 && T <= 1024, "bad CTA size");
     static_assert(H % RI == 0, "bad tiling");
 
-    // bx: row-item group, by: 0 = displacement map (fields 0,1), 1 = normal map (fields 2,3), bz: item
     template <class Exec>
     static WSO_HD void run(Exec& ex, float2* smem, int bx, int by, int bz, const LaunchArgs& args) {
         const BatchItem item = args.items[bz];
-        const float lambda = args.tiles[item.tile].lambda;
         const float2* Wit = args.W + (size_t)bz * ((size_t)H * 4 * N);
 
         // ---- first stage straight from global memory (W rows are contiguous) ---------------------
@@ -283,82 +340,113 @@ struct Pass2 {
             constexpr int R = Plan<LOGN>::R[0];
             using St = Stage<N, B, R, 1>;
             ex.each([&](int tid, ThreadState& st) {
+                const int line = tid / G;
+                const int mp = bx * RI + line / LPI;
+                const int f = HEIGHT_ONLY ? 0 : by * 2 + (line % LPI);
+                const float2* src = Wit + ((size_t)mp * 4 + f) * N;
 #pragma unroll
                 for (int i = 0; i < St::NB; ++i) {
-                    const int line = tid / St::G;
-                    const int j = tid % St::G + St::G * i;
-                    const int mp = bx * RI + (line >> 1);
-                    const int f = by * 2 + (line & 1);
-                    const float2* src = Wit + ((size_t)mp * 4 + f) * N;
+                    const int j = tid % G + G * i;
 #pragma unroll
                     for (int r = 0; r < R; ++r) st.v[i * R + r] = src[slot_of_column(j + r * St::JN, N)];
                 }
                 St::twiddle_dft(args.tw, tid, st);
                 St::store(smem, tid, st);
             });
-            ex.template sync_group<St::G, T>(1);
+            ex.template sync_group<G, T>(1);
             if constexpr (Plan<LOGN>::S > 1) RunStages<LOGN, B, 1, R, Exec>::run(ex, smem, args.tw);
         }
         // the pack phase of a row item reads both of its lines: barrier over that pair of line groups
-        constexpr int G2 = 2 * (N / kValsPerThread);
-        ex.template sync_group<G2, T>(1 + ((N / kValsPerThread) > 32 ? B : 0));
+        if constexpr (LPI == 2) ex.template sync_group<GI, T>(1 + (G > 32 ? B : 0));
 
-        // ---- pack: each transformed line pair yields output rows m' and N-m' ---------------------
-        float4* out = (by == 0 ? args.disp : args.norm) + (size_t)item.slot * ((size_t)N * N);
-        ex.each([&](int tid, ThreadState& st) {
-            float mn = kInitMin, mx = kInitMax;
-            const int ri = tid / G2;                  // the row item this thread's line pair belongs to
-            for (int c = tid % G2; c < N; c += G2) {  // output column n'
-                const int cm = (N - c) & (N - 1);     // mirrored column
+        if constexpr (HEIGHT_ONLY) {
+            ex.each([&](int tid, ThreadState& st) {
+                float mn = kInitMin, mx = kInitMax;
+                const int ri = tid / GI, lt = tid % GI;
+                const int mp = bx * RI + ri;
+                const float2* l0 = smem + ri * LS;
+                // (-1)^(row+col): loop invariant when the column stride GI is even (N >= 32)
+                float s = ((mp + lt) & 1) ? -1.0f : 1.0f;
+                if (mp != 0) {
+                    for (int c = lt; c < N; c += GI) {
+                        if (GI & 1) s = ((mp + c) & 1) ? -1.0f : 1.0f;
+                        const float h = rmul(l0[pad_idx(c)].x, s);
+                        mn = h < mn ? h : mn;
+                        mx = h > mx ? h : mx;
+                    }
+                } else {  // rows 0 and N/2 were transformed as one complex line
+                    for (int c = lt; c < N; c += GI) {
+                        if (GI & 1) s = (c & 1) ? -1.0f : 1.0f;
+                        const float2 a = l0[pad_idx(c)], m = l0[pad_idx((N - c) & (N - 1))];
+                        const float hA = rmul(0.5f * (a.x + m.x), s), hB = rmul(0.5f * (a.y + m.y), s);
+                        mn = hA < mn ? hA : mn; mx = hA > mx ? hA : mx;
+                        mn = hB < mn ? hB : mn; mx = hB > mx ? hB : mx;
+                    }
+                }
+                st.v[0] = make_float2(mn, mx);
+            });
+            ex.commit_minmax(args.minmax + 2 * item.slot);
+        } else {
+            // ---- pack: each transformed line pair yields output rows m' and N-m' -----------------
+            // reference: WSTessendorf.cpp:385-437 (sign, lambda, packing) and :443-455 (normalisation)
+            const float lambda = args.tiles[item.tile].lambda;
+            const float amp = amplitude_of(args.minmax[2 * item.slot], args.minmax[2 * item.slot + 1]);
+            const float inv_amp = rdiv(1.0f, amp);
+            if (bx == 0 && by == 0) {
+                ex.each([&](int tid, ThreadState&) {
+                    if (tid == 0) args.amp_out[item.slot] = amp;
+                });
+            }
+            float4* out = (by == 0 ? args.disp : args.norm) + (size_t)item.slot * ((size_t)N * N);
+            ex.each([&](int tid, ThreadState&) {
+                const int ri = tid / GI, lt = tid % GI;
                 const int mp = bx * RI + ri;
                 const float2* l0 = smem + (ri * 2 + 0) * LS;
-                const float2* l1 = smem + (ri * 2 + 1) * LS;
-                float2 a0 = l0[pad_idx(c)], a1 = l1[pad_idx(c)];  // F at (rowA, c)
-                float2 b0, b1;                                    // F at (rowB, colB)
-                int rowA, rowB, colB;
-                if (mp == 0) {
+                const float2* l1 = l0 + LS;
+                // (-1)^(row+col) is the same for both output rows and every column this thread visits
+                const float s = ((mp + lt) & 1) ? -1.0f : 1.0f;
+                const float sl = rmul(s, lambda);
+                if (mp != 0) {
+                    float4* outA = out + (size_t)mp * N;
+                    float4* outB = out + (size_t)(N - mp) * N;
+                    for (int c = lt; c < N; c += GI) {
+                        const int e = pad_idx(c);
+                        const float2 a0 = l0[e], a1 = l1[e];
+                        const int cm = (N - c) & (N - 1);   // row N-m' is the conjugate mirror of row m'
+                        if (by == 0) {
+                            const float y = rmul(rmul(a0.x, s), inv_amp);
+                            const float x = rmul(sl, a0.y), z = rmul(sl, a1.y);
+                            outA[c] = make_float4(x, y, z, 1.0f);
+                            outB[cm] = make_float4(-x, y, -z, 1.0f);
+                        } else {
+                            const float4 ta = make_float4(s * a0.y, s * a1.y, s * a0.x, s * a1.x);
+                            outA[c] = ta;
+                            outB[cm] = make_float4(-ta.x, -ta.y, ta.z, ta.w);
+                        }
+                    }
+                } else {
                     // rows 0 and N/2 were transformed as one complex line: separate them
-                    const float2 m0 = l0[pad_idx(cm)], m1 = l1[pad_idx(cm)];
-                    b0 = make_float2(0.5f * (a0.y + m0.y), -0.5f * (a0.x - m0.x));
-                    b1 = make_float2(0.5f * (a1.y + m1.y), -0.5f * (a1.x - m1.x));
-                    a0 = make_float2(0.5f * (a0.x + m0.x), 0.5f * (a0.y - m0.y));
-                    a1 = make_float2(0.5f * (a1.x + m1.x), 0.5f * (a1.y - m1.y));
-                    rowA = 0; rowB = H; colB = c;
-                } else {
-                    b0 = cconj(a0);
-                    b1 = cconj(a1);
-                    rowA = mp; rowB = N - mp; colB = cm;
+                    float4* outA = out;
+                    float4* outB = out + (size_t)H * N;
+                    for (int c = lt; c < N; c += GI) {
+                        const int e = pad_idx(c), em = pad_idx((N - c) & (N - 1));
+                        const float2 p0 = l0[e], p1 = l1[e], m0 = l0[em], m1 = l1[em];
+                        const float2 a0 = make_float2(0.5f * (p0.x + m0.x), 0.5f * (p0.y - m0.y));
+                        const float2 a1 = make_float2(0.5f * (p1.x + m1.x), 0.5f * (p1.y - m1.y));
+                        const float2 b0 = make_float2(0.5f * (p0.y + m0.y), -0.5f * (p0.x - m0.x));
+                        const float2 b1 = make_float2(0.5f * (p1.y + m1.y), -0.5f * (p1.x - m1.x));
+                        if (by == 0) {
+                            outA[c] = make_float4(rmul(sl, a0.y), rmul(rmul(a0.x, s), inv_amp), rmul(sl, a1.y), 1.0f);
+                            outB[c] = make_float4(rmul(sl, b0.y), rmul(rmul(b0.x, s), inv_amp), rmul(sl, b1.y), 1.0f);
+                        } else {
+                            outA[c] = make_float4(s * a0.y, s * a1.y, s * a0.x, s * a1.x);
+                            outB[c] = make_float4(s * b0.y, s * b1.y, s * b0.x, s * b1.x);
+                        }
+                    }
                 }
-                // reference: WSTessendorf.cpp:385-437 — sign = (-1)^(m+n)
-                const float sA = ((rowA + c) & 1) ? -1.0f : 1.0f;
-                const float sB = ((rowB + colB) & 1) ? -1.0f : 1.0f;
-                float4 ta, tb;
-                if (by == 0) {
-                    const float hA = rmul(a0.x, sA), hB = rmul(b0.x, sB);
-                    mn = hA < mn ? hA : mn; mx = hA > mx ? hA : mx;
-                    mn = hB < mn ? hB : mn; mx = hB > mx ? hB : mx;
-                    ta = make_float4(rmul(rmul(sA, lambda), a0.y), hA, rmul(rmul(sA, lambda), a1.y), 1.0f);
-                    tb = make_float4(rmul(rmul(sB, lambda), b0.y), hB, rmul(rmul(sB, lambda), b1.y), 1.0f);
-                } else {
-                    ta = make_float4(sA * a0.y, sA * a1.y, sA * a0.x, sA * a1.x);
-                    tb = make_float4(sB * b0.y, sB * b1.y, sB * b0.x, sB * b1.x);
-                }
-                out[(size_t)rowA * N + c] = ta;
-                out[(size_t)rowB * N + colB] = tb;
-            }
-            st.v[0] = make_float2(mn, mx);
-        });
-        if (by == 0) ex.commit_minmax(args.minmax + 2 * item.slot);
+            });
+        }
     }
 };
-
-// -------------------------------------------------------------------------------------------------
-// K3 — reference: NormalizeHeights, WSTessendorf.cpp:443-455
-// -------------------------------------------------------------------------------------------------
-WSO_HD float amplitude_of(float mn, float mx) {
-    const float a = mn < 0.0f ? -mn : mn;
-    const float b = mx < 0.0f ? -mx : mx;
-    return a > b ? a : b;
-}
 
 }  // namespace wso

@@ -9,9 +9,9 @@ struct LaunchArgs;
 static constexpr int kMinLogN = 4;   // 16
 static constexpr int kMaxLogN = 13;  // 8192 (single-CTA line transforms; larger grids: slab path)
 
-// Enqueue K1 (evolve + first transform), K2 (second transform + pack) and K3 (normalise) for
+// Enqueue K1 (evolve + first transform), K2h (height extrema) and K2 (second transform + pack) for
 // n_items tile-frames described by args.items[0..n_items).
-// ev: NULL, or 4 events recorded before K1, between the kernels and after K3 (opt-in profiling).
+// ev: NULL, or 4 events recorded before K1, between the kernels and after K2 (opt-in profiling).
 cudaError_t launch_compute_waves(int logn, const LaunchArgs& args, int n_items, cudaStream_t stream,
                                  bool first_use, cudaEvent_t* ev);
 int kernels_per_launch();
