@@ -1,6 +1,7 @@
 // wso_api.cu — the C ABI (include/wsocean.h): context, buffers, Prepare(), batching, host copies.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -34,6 +35,8 @@ struct wso_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t aux_stream = nullptr;  // second compute lane: odd chunks of a batch (fills the tails of the even ones)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaStream_t stream = nullptr;  // the one kernels run on (own_stream unless wso_set_stream)
     cudaEvent_t ev_chunk[2] = {nullptr, nullptr};
     cudaEvent_t ev_copied[2] = {nullptr, nullptr};
@@ -139,7 +142,12 @@ int allocate_for_size(wso_ctx* c, uint32_t n) {
     // chunk: tile-frames per launch.  Keep the W scratch of one chunk around 48 MB so it stays in the
     // 126 MB L2 between K1 and K2.
     const size_t w_item = n2 * 16;
-    size_t chunk = (48u << 20) / w_item;
+    size_t budget_mb = 48;
+    if (const char* env = std::getenv("WSO_W_BUDGET_MB")) {
+        const long v = std::atol(env);
+        if (v > 0 && v <= 65536) budget_mb = (size_t)v;
+    }
+    size_t chunk = (budget_mb << 20) / w_item;
     if (chunk < 1) chunk = 1;
     if (chunk > (size_t)wso::kMaxChunk) chunk = wso::kMaxChunk;
     if (chunk > c->max_slots) chunk = c->max_slots;
@@ -261,7 +269,7 @@ int begin_prepare(wso_ctx* c, uint32_t tile) {
 }
 
 int enqueue_chunk(wso_ctx* c, uint32_t n_items, const uint32_t* tiles, const float* t, uint32_t first_slot,
-                  int wbuf) {
+                  int wbuf, cudaStream_t stream) {
     LaunchArgs args;
     args.tiles = c->d_tiles;
     args.tw = c->d_tw;
@@ -291,7 +299,7 @@ int enqueue_chunk(wso_ctx* c, uint32_t n_items, const uint32_t* tiles, const flo
         c->prof_launches += 1;
         c->prof_items += n_items;
     }
-    cudaError_t e = wso::launch_compute_waves(c->logn, args, (int)n_items, c->stream, c->first_use, ev);
+    cudaError_t e = wso::launch_compute_waves(c->logn, args, (int)n_items, stream, c->first_use, ev);
     if (e != cudaSuccess) return fail_cuda(c, e, "kernel launch");
     c->first_use = false;
     c->launches += (uint64_t)wso::kernels_per_launch();
@@ -354,6 +362,9 @@ int wso_create(const wso_params* p, int device, uint32_t max_tiles, uint32_t max
         if ((e = cudaSetDevice(device)) != cudaSuccess) { rc = fail_cuda(nullptr, e, "cudaSetDevice"); break; }
         if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess) { rc = fail_cuda(nullptr, e, "cudaStreamCreate"); break; }
         if ((e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) { rc = fail_cuda(nullptr, e, "cudaStreamCreate"); break; }
+        if ((e = cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking)) != cudaSuccess) { rc = fail_cuda(nullptr, e, "cudaStreamCreate"); break; }
+        if ((e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming)) != cudaSuccess) { rc = fail_cuda(nullptr, e, "cudaEventCreate"); break; }
+        if ((e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming)) != cudaSuccess) { rc = fail_cuda(nullptr, e, "cudaEventCreate"); break; }
         for (int i = 0; i < 2; ++i) {
             if ((e = cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming)) != cudaSuccess) break;
             if ((e = cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming)) != cudaSuccess) break;
@@ -376,7 +387,11 @@ int wso_destroy(wso_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    if (c->aux_stream) cudaStreamSynchronize(c->aux_stream);
     free_device_buffers(c);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
     for (int i = 0; i < 2; ++i) {
         if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]);
         if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
@@ -451,12 +466,25 @@ int wso_compute_batch(wso_ctx* c, uint32_t n, const uint32_t* tiles, const float
     if (rc != WSO_OK) return rc;
     WSO_CUDA(c, cudaSetDevice(c->device));
     if ((rc = push_lambdas(c)) != WSO_OK) return rc;
-    int wbuf = 0;
+    // Two compute lanes: even chunks on the caller-visible stream, odd chunks on an internal one, each lane with
+    // its own W scratch.  Chunks are independent, so the second lane's kernels fill the partial last wave and the
+    // launch gaps of the first.  Fork/join events keep everything ordered with respect to c->stream.
+    const bool two_lanes = n > c->chunk;
+    if (two_lanes) {
+        WSO_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));
+        WSO_CUDA(c, cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
+    }
+    int lane = 0;
     for (uint32_t done = 0; done < n; done += c->chunk) {
         const uint32_t m = (n - done < c->chunk) ? (n - done) : c->chunk;
-        rc = enqueue_chunk(c, m, tiles ? tiles + done : nullptr, t + done, first_slot + done, wbuf);
+        rc = enqueue_chunk(c, m, tiles ? tiles + done : nullptr, t + done, first_slot + done, lane,
+                           lane ? c->aux_stream : c->stream);
         if (rc != WSO_OK) return rc;
-        wbuf ^= 1;
+        lane ^= 1;
+    }
+    if (two_lanes) {
+        WSO_CUDA(c, cudaEventRecord(c->ev_join, c->aux_stream));
+        WSO_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
     }
     return WSO_OK;
 }
@@ -465,6 +493,7 @@ int wso_sync(wso_ctx* c) {
     if (!c) return WSO_ERR_INVALID_ARG;
     WSO_CUDA(c, cudaSetDevice(c->device));
     WSO_CUDA(c, cudaStreamSynchronize(c->stream));
+    WSO_CUDA(c, cudaStreamSynchronize(c->aux_stream));
     WSO_CUDA(c, cudaStreamSynchronize(c->copy_stream));
     return WSO_OK;
 }
@@ -492,7 +521,7 @@ int wso_compute(wso_ctx* c, float t, float* amplitude) {
     if (rc != WSO_OK) return rc;
     WSO_CUDA(c, cudaSetDevice(c->device));
     if ((rc = push_lambdas(c)) != WSO_OK) return rc;
-    if ((rc = enqueue_chunk(c, 1, nullptr, &t, 0, 0)) != WSO_OK) return rc;
+    if ((rc = enqueue_chunk(c, 1, nullptr, &t, 0, 0, c->stream)) != WSO_OK) return rc;
     const size_t bytes = sizeof(float4) * (size_t)c->n * c->n;
     WSO_CUDA(c, cudaMemcpyAsync(c->h_disp, c->d_disp, bytes, cudaMemcpyDeviceToHost, c->stream));
     WSO_CUDA(c, cudaMemcpyAsync(c->h_norm, c->d_norm, bytes, cudaMemcpyDeviceToHost, c->stream));
@@ -535,10 +564,15 @@ int wso_compute_to_host(wso_ctx* c, uint32_t n, const uint32_t* tiles, const flo
         const int b = k & 1;
         const uint32_t slot0 = (uint32_t)b * c->chunk;
         // the slots (and W buffer) of parity b are free once the copy issued two chunks ago is done
-        if (k >= 2) WSO_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
-        rc = enqueue_chunk(c, m, tiles ? tiles + done : nullptr, t + done, slot0, b);
+        cudaStream_t lane = b ? c->aux_stream : c->stream;
+        if (k == 1) {  // first use of the second lane: order it after whatever preceded this call on c->stream
+            WSO_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));
+            WSO_CUDA(c, cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
+        }
+        if (k >= 2) WSO_CUDA(c, cudaStreamWaitEvent(lane, c->ev_copied[b], 0));
+        rc = enqueue_chunk(c, m, tiles ? tiles + done : nullptr, t + done, slot0, b, lane);
         if (rc != WSO_OK) return rc;
-        WSO_CUDA(c, cudaEventRecord(c->ev_chunk[b], c->stream));
+        WSO_CUDA(c, cudaEventRecord(c->ev_chunk[b], lane));
         WSO_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_chunk[b], 0));
         WSO_CUDA(c, cudaMemcpyAsync(disp_host + (size_t)done * texels * 4, c->d_disp + (size_t)slot0 * texels,
                                     map_bytes * m, cudaMemcpyDeviceToHost, c->copy_stream));
@@ -551,6 +585,7 @@ int wso_compute_to_host(wso_ctx* c, uint32_t n, const uint32_t* tiles, const flo
         WSO_CUDA(c, cudaEventRecord(c->ev_copied[b], c->copy_stream));
     }
     WSO_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+    WSO_CUDA(c, cudaStreamSynchronize(c->aux_stream));
     WSO_CUDA(c, cudaStreamSynchronize(c->stream));
     for (uint32_t i = 0; i < n; ++i) {
         if (amplitude) amplitude[i] = small[i];
