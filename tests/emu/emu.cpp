@@ -44,13 +44,25 @@ static int run_cfg(const float* amp_t, const float* omega_t, const float* kv, fl
             }
             rec[i] = make_float4(amp_t[2 * i], amp_t[2 * i + 1], inv, wf);
         }
+    const int hN = N / 2;
+    std::vector<float4> recs((size_t)hN * hN * 2, make_float4(0.f, 0.f, 0.f, 0.f));
+    bool pairs_ok = true;
+    for (int j = 1; j < hN; ++j)
+        for (int i = 1; i < hN; ++i) {
+            const float4 a0 = rec[(size_t)j * N + i], a3 = rec[(size_t)(N - j) * N + (N - i)];
+            const float4 a1 = rec[(size_t)(N - j) * N + i], a2 = rec[(size_t)j * N + (N - i)];
+            if (std::memcmp(&a0.w, &a3.w, 4) != 0 || std::memcmp(&a1.w, &a2.w, 4) != 0) pairs_ok = false;
+            recs[((size_t)j * hN + i) * 2 + 0] = make_float4(a0.x + a3.x, a0.y + a3.y, a0.z, a0.w);
+            recs[((size_t)j * hN + i) * 2 + 1] = make_float4(a1.x + a2.x, a1.y + a2.y, a1.z, a1.w);
+        }
     TileDev td;
     td.h0 = rec.data();
+    td.hs = recs.data();
     td.kv = kv;
     td.lambda = lambda;
     td.omega0 = omega0;
     td.table_len = table_ok ? jmax + 1 : 0;
-    td.pad_ = 0;
+    td.use_pairs = pairs_ok ? 1 : 0;
     std::vector<float2> W((size_t)H * 4 * N);
     LaunchArgs args;
     std::memset(&args, 0, sizeof(args));

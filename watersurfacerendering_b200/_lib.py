@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libwsocean.so")
+# WSO_LIB_PATH: tuning sweeps point this at a variant build of the same library (tools/tune_build.sh)
+LIB_PATH = os.environ.get("WSO_LIB_PATH") or os.path.join(PKG_DIR, "libwsocean.so")
 
 WSO_OK = 0
 WSO_ERR_INVALID_ARG = -1

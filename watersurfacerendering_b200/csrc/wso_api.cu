@@ -49,6 +49,7 @@ struct wso_ctx {
     std::vector<Tile> tiles;
     // device
     float4* d_h0 = nullptr;      // [tile][n][m] (amp.re, amp.im, 1/|k|, omega or j)
+    float4* d_hs = nullptr;      // [tile][j][i][2] pair-summed records (see TileDev::hs)
     float* d_kv = nullptr;       // [tile][N]
     TileDev* d_tiles = nullptr;  // [tile]
     float2* d_tw = nullptr;      // [N]
@@ -115,6 +116,7 @@ bool valid_params(const wso_params& p) {
 
 void free_device_buffers(wso_ctx* c) {
     cudaFree(c->d_h0); c->d_h0 = nullptr;
+    cudaFree(c->d_hs); c->d_hs = nullptr;
     cudaFree(c->d_kv); c->d_kv = nullptr;
     cudaFree(c->d_tiles); c->d_tiles = nullptr;
     cudaFree(c->d_tw); c->d_tw = nullptr;
@@ -153,6 +155,7 @@ int allocate_for_size(wso_ctx* c, uint32_t n) {
     if (chunk > c->max_slots) chunk = c->max_slots;
     c->chunk = (uint32_t)chunk;
     WSO_CUDA(c, cudaMalloc(&c->d_h0, sizeof(float4) * n2 * c->max_tiles));
+    WSO_CUDA(c, cudaMalloc(&c->d_hs, sizeof(float4) * (n2 / 2) * c->max_tiles));
     WSO_CUDA(c, cudaMalloc(&c->d_kv, sizeof(float) * n * c->max_tiles));
     WSO_CUDA(c, cudaMalloc(&c->d_tiles, sizeof(TileDev) * c->max_tiles));
     WSO_CUDA(c, cudaMalloc(&c->d_tw, sizeof(float2) * n));
@@ -178,10 +181,12 @@ int allocate_for_size(wso_ctx* c, uint32_t n) {
     c->h_tiles.assign(c->max_tiles, TileDev{});
     for (uint32_t t = 0; t < c->max_tiles; ++t) {
         c->h_tiles[t].h0 = c->d_h0 + n2 * t;
+        c->h_tiles[t].hs = c->d_hs + (n2 / 2) * t;
         c->h_tiles[t].kv = c->d_kv + (size_t)n * t;
         c->h_tiles[t].lambda = c->tiles[t].params.lambda;
         c->h_tiles[t].omega0 = 0.0f;
         c->h_tiles[t].table_len = 0;
+        c->h_tiles[t].use_pairs = 0;
         c->tiles[t].is_prepared = false;
         c->tiles[t].h0.clear();
     }
@@ -229,12 +234,26 @@ int upload_h0(wso_ctx* c, uint32_t tile, const wso_h0_record* h0) {
             }
             rec[(size_t)k * n + m] = make_float4(r.amp_re, r.amp_im, inv, wfield);
         }
+    // pair-summed records for the interior (i,j >= 1): amplitude h0(k) + h0(-k); 1/|k| and omega are even in k
+    const uint32_t hN = n / 2;
+    std::vector<float4> recs((size_t)hN * hN * 2, make_float4(0.f, 0.f, 0.f, 0.f));
+    bool pairs_ok = true;  // needs omega(k) == omega(-k): true for any dispersion that depends on |k| only
+    for (uint32_t j = 1; j < hN; ++j)
+        for (uint32_t i = 1; i < hN; ++i) {
+            const float4 a0 = rec[(size_t)j * n + i], a3 = rec[(size_t)(n - j) * n + (n - i)];
+            const float4 a1 = rec[(size_t)(n - j) * n + i], a2 = rec[(size_t)j * n + (n - i)];
+            if (std::memcmp(&a0.w, &a3.w, 4) != 0 || std::memcmp(&a1.w, &a2.w, 4) != 0) pairs_ok = false;
+            recs[((size_t)j * hN + i) * 2 + 0] = make_float4(a0.x + a3.x, a0.y + a3.y, a0.z, a0.w);
+            recs[((size_t)j * hN + i) * 2 + 1] = make_float4(a1.x + a2.x, a1.y + a2.y, a1.z, a1.w);
+        }
     WSO_CUDA(c, cudaSetDevice(c->device));
     WSO_CUDA(c, cudaStreamSynchronize(c->stream));
     WSO_CUDA(c, cudaMemcpy(c->d_h0 + n2 * tile, rec.data(), sizeof(float4) * n2, cudaMemcpyHostToDevice));
+    WSO_CUDA(c, cudaMemcpy(c->d_hs + (n2 / 2) * tile, recs.data(), sizeof(float4) * (n2 / 2), cudaMemcpyHostToDevice));
     WSO_CUDA(c, cudaMemcpy(c->d_kv + (size_t)n * tile, kv.data(), sizeof(float) * n, cudaMemcpyHostToDevice));
     c->h_tiles[tile].omega0 = omega0;
     c->h_tiles[tile].table_len = table_ok ? jmax + 1 : 0;
+    c->h_tiles[tile].use_pairs = pairs_ok ? 1 : 0;
     WSO_CUDA(c, cudaMemcpy(c->d_tiles + tile, &c->h_tiles[tile], sizeof(TileDev), cudaMemcpyHostToDevice));
     Tile& tl = c->tiles[tile];
     if (tl.h0.data() != h0) tl.h0.assign(h0, h0 + n2);
@@ -469,7 +488,7 @@ int wso_compute_batch(wso_ctx* c, uint32_t n, const uint32_t* tiles, const float
     // Two compute lanes: even chunks on the caller-visible stream, odd chunks on an internal one, each lane with
     // its own W scratch.  Chunks are independent, so the second lane's kernels fill the partial last wave and the
     // launch gaps of the first.  Fork/join events keep everything ordered with respect to c->stream.
-    const bool two_lanes = n > c->chunk;
+    const bool two_lanes = n > c->chunk && !c->profiling;  // per-kernel event timing wants the kernels serialised
     if (two_lanes) {
         WSO_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));
         WSO_CUDA(c, cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
@@ -480,7 +499,7 @@ int wso_compute_batch(wso_ctx* c, uint32_t n, const uint32_t* tiles, const float
         rc = enqueue_chunk(c, m, tiles ? tiles + done : nullptr, t + done, first_slot + done, lane,
                            lane ? c->aux_stream : c->stream);
         if (rc != WSO_OK) return rc;
-        lane ^= 1;
+        if (two_lanes) lane ^= 1;
     }
     if (two_lanes) {
         WSO_CUDA(c, cudaEventRecord(c->ev_join, c->aux_stream));

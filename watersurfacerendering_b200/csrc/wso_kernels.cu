@@ -14,9 +14,28 @@ template <> struct Cfg<5>  { static constexpr int CP = 8, NF = 4, RI = 8, RH = 1
 template <> struct Cfg<6>  { static constexpr int CP = 8, NF = 4, RI = 8, RH = 16; };
 template <> struct Cfg<7>  { static constexpr int CP = 4, NF = 4, RI = 8, RH = 16; };
 template <> struct Cfg<8>  { static constexpr int CP = 4, NF = 4, RI = 4, RH = 8; };
-template <> struct Cfg<9>  { static constexpr int CP = 4, NF = 2, RI = 2, RH = 4; };
-template <> struct Cfg<10> { static constexpr int CP = 4, NF = 2, RI = 4, RH = 8; };
-template <> struct Cfg<11> { static constexpr int CP = 4, NF = 1, RI = 2, RH = 4; };
+// (the WSO_TUNE_* macros exist for tuning sweeps: tools/tune_build.sh builds variant libraries)
+#ifndef WSO_TUNE_CP9
+#define WSO_TUNE_CP9 4
+#define WSO_TUNE_NF9 4
+#define WSO_TUNE_RI9 4
+#define WSO_TUNE_RH9 8
+#endif
+#ifndef WSO_TUNE_CP10
+#define WSO_TUNE_CP10 4
+#define WSO_TUNE_NF10 2
+#define WSO_TUNE_RI10 4
+#define WSO_TUNE_RH10 8
+#endif
+#ifndef WSO_TUNE_CP11
+#define WSO_TUNE_CP11 4
+#define WSO_TUNE_NF11 2
+#define WSO_TUNE_RI11 2
+#define WSO_TUNE_RH11 4
+#endif
+template <> struct Cfg<9>  { static constexpr int CP = WSO_TUNE_CP9, NF = WSO_TUNE_NF9, RI = WSO_TUNE_RI9, RH = WSO_TUNE_RH9; };
+template <> struct Cfg<10> { static constexpr int CP = WSO_TUNE_CP10, NF = WSO_TUNE_NF10, RI = WSO_TUNE_RI10, RH = WSO_TUNE_RH10; };
+template <> struct Cfg<11> { static constexpr int CP = WSO_TUNE_CP11, NF = WSO_TUNE_NF11, RI = WSO_TUNE_RI11, RH = WSO_TUNE_RH11; };
 template <> struct Cfg<12> { static constexpr int CP = 4, NF = 1, RI = 2, RH = 4; };
 template <> struct Cfg<13> { static constexpr int CP = 2, NF = 1, RI = 1, RH = 2; };
 

@@ -26,11 +26,17 @@ struct TileDev {
     //   w   = quantised dispersion omega (WSTessendorf.h:284-287), or - when table_len > 0 - its integer
     //         multiple j of the base frequency (omega == fl(float(j)*omega0) exactly, checked at Prepare)
     const float4* h0;
+    // [j][i][2] for column pair j = (j, N-j) and row pair i = (i, N-i), i,j in [0, N/2): the same record with
+    // the amplitude replaced by the sum over the mirror pair, h0(k) + h0(-k):
+    //   [0]: k = (m=i, n=j)     [1]: k = (m=i, n=N-j)
+    // Only Re FFT is kept, so away from the index-0 / N/2 lines every field depends on h~ only through
+    // h~(k) + h~(-k) (same omega for k and -k): one record and one (cos,sin) lookup serve two wave vectors.
+    const float4* hs;
     const float* kv;     // [N]: kv[i] = (float)(M_PI*(2.0f*i-N)/L)  (reference: WSTessendorf.cpp:75-80)
     float lambda;        // displacement scale (reference: WSTessendorf.h:181)
     float omega0;        // base frequency (float)(2*pi/T)
     int table_len;       // j_max+1 when the per-frame sincos table is usable, else 0
-    int pad_;
+    int use_pairs;       // 1 when omega(k) == omega(-k) everywhere (always true for Prepare()-built h0): hs is valid
 };
 
 struct BatchItem {
@@ -172,15 +178,13 @@ struct Pass1 {
                                    int cp, int i, int j) {
         const int mA = i, mB = (i == 0) ? H : N - i;
         const int nA = j, nB = (j == 0) ? H : N - j;
-        const float4 q0 = td.h0[nA * N + mA], q1 = td.h0[nB * N + mA];
-        const float4 q2 = td.h0[nA * N + mB], q3 = td.h0[nB * N + mB];
-        const float h0 = eval_height<TABLE>(q0, table, t), h1 = eval_height<TABLE>(q1, table, t);
-        const float h2 = eval_height<TABLE>(q2, table, t), h3 = eval_height<TABLE>(q3, table, t);
         const float kxA = td.kv[nA], kxB = td.kv[nB], kzA = td.kv[mA], kzB = td.kv[mB];
         const int eA = pad_idx(mA), eB = pad_idx(mB);
         float2 a, b;
-        if (i != 0 && j != 0) {
-            const float s0 = 0.5f * (h0 + h3), s1 = 0.5f * (h1 + h2);
+        if (i != 0 && j != 0 && td.use_pairs) {
+            // interior: pair-summed records, s = (h~(k) + h~(-k)) / 2
+            const float4 q0 = td.hs[((size_t)j * H + i) * 2 + 0], q1 = td.hs[((size_t)j * H + i) * 2 + 1];
+            const float s0 = 0.5f * eval_height<TABLE>(q0, table, t), s1 = 0.5f * eval_height<TABLE>(q1, table, t);
             if (NF == 4 || (NF == 2 && fg == 0) || (NF == 1 && fg == 0)) {
                 pack_interior<0>(s0, kxA, kzA, q0.z, s1, kxB, kzA, q1.z, &a, &b);
                 put<0>(smem, 0, cp, eA, eB, a, b);
@@ -198,6 +202,10 @@ struct Pass1 {
                 put<3>(smem, NF == 4 ? 3 : (NF == 2 ? 1 : 0), cp, eA, eB, a, b);
             }
         } else {
+            const float4 q0 = td.h0[nA * N + mA], q1 = td.h0[nB * N + mA];
+            const float4 q2 = td.h0[nA * N + mB], q3 = td.h0[nB * N + mB];
+            const float h0 = eval_height<TABLE>(q0, table, t), h1 = eval_height<TABLE>(q1, table, t);
+            const float h2 = eval_height<TABLE>(q2, table, t), h3 = eval_height<TABLE>(q3, table, t);
             const int mask = ((i != 0) ? 2 : 0) | ((j != 0) ? 1 : 0);
             Point pt[4];
             pt[0] = Point{h0, kxA, kzA, rmul(kxA, q0.z), rmul(kzA, q0.z)};
