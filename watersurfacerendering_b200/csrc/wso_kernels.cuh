@@ -172,61 +172,100 @@ struct Pass1 {
         smem[(fl * CP + cp) * LS + eB] = b;
     }
 
-    // one work item = rows (mA,mB) x columns (nA,nB): 4 wave vectors, NF packed fields each
+    // Writes the NF packed fields of one interior work item given s = (h~(k) + h~(-k)) / 2 at its two wave vectors.
+    static WSO_HD void pack_interior_item(float2* smem, int fg, int cp, int eA, int eB, float s0, float s1,
+                                          float kxA, float kxB, float kzA, float inv0, float inv1) {
+        float2 a, b;
+        if (NF == 4 || (NF == 2 && fg == 0) || (NF == 1 && fg == 0)) {
+            pack_interior<0>(s0, kxA, kzA, inv0, s1, kxB, kzA, inv1, &a, &b);
+            put<0>(smem, 0, cp, eA, eB, a, b);
+        }
+        if (NF == 4 || (NF == 2 && fg == 0) || (NF == 1 && fg == 1)) {
+            pack_interior<1>(s0, kxA, kzA, inv0, s1, kxB, kzA, inv1, &a, &b);
+            put<1>(smem, NF == 1 ? 0 : 1, cp, eA, eB, a, b);
+        }
+        if (NF == 4 || (NF == 2 && fg == 1) || (NF == 1 && fg == 2)) {
+            pack_interior<2>(s0, kxA, kzA, inv0, s1, kxB, kzA, inv1, &a, &b);
+            put<2>(smem, NF == 4 ? 2 : 0, cp, eA, eB, a, b);
+        }
+        if (NF == 4 || (NF == 2 && fg == 1) || (NF == 1 && fg == 3)) {
+            pack_interior<3>(s0, kxA, kzA, inv0, s1, kxB, kzA, inv1, &a, &b);
+            put<3>(smem, NF == 4 ? 3 : (NF == 2 ? 1 : 0), cp, eA, eB, a, b);
+        }
+    }
+
+    // one work item on the index-0 / N/2 lines (or any item when the pair records are unusable):
+    // rows (mA,mB) x columns (nA,nB) = 4 wave vectors from the per-point records, general mirror pattern
     template <bool TABLE>
-    static WSO_HD void evolve_item(const TileDev& td, const float2* table, float t, int fg, float2* smem,
-                                   int cp, int i, int j) {
+    static WSO_HD void evolve_item_general(const TileDev& td, const float2* table, float t, int fg, float2* smem,
+                                           int cp, int i, int j) {
         const int mA = i, mB = (i == 0) ? H : N - i;
         const int nA = j, nB = (j == 0) ? H : N - j;
         const float kxA = td.kv[nA], kxB = td.kv[nB], kzA = td.kv[mA], kzB = td.kv[mB];
         const int eA = pad_idx(mA), eB = pad_idx(mB);
+        const float4 q0 = td.h0[nA * N + mA], q1 = td.h0[nB * N + mA];
+        const float4 q2 = td.h0[nA * N + mB], q3 = td.h0[nB * N + mB];
+        const float h0 = eval_height<TABLE>(q0, table, t), h1 = eval_height<TABLE>(q1, table, t);
+        const float h2 = eval_height<TABLE>(q2, table, t), h3 = eval_height<TABLE>(q3, table, t);
+        const int mask = ((i != 0) ? 2 : 0) | ((j != 0) ? 1 : 0);
+        Point pt[4];
+        pt[0] = Point{h0, kxA, kzA, rmul(kxA, q0.z), rmul(kzA, q0.z)};
+        pt[1] = Point{h1, kxB, kzA, rmul(kxB, q1.z), rmul(kzA, q1.z)};
+        pt[2] = Point{h2, kxA, kzB, rmul(kxA, q2.z), rmul(kzB, q2.z)};
+        pt[3] = Point{h3, kxB, kzB, rmul(kxB, q3.z), rmul(kzB, q3.z)};
         float2 a, b;
-        if (i != 0 && j != 0 && td.use_pairs) {
-            // interior: pair-summed records, s = (h~(k) + h~(-k)) / 2
-            const float4 q0 = td.hs[((size_t)j * H + i) * 2 + 0], q1 = td.hs[((size_t)j * H + i) * 2 + 1];
-            const float s0 = 0.5f * eval_height<TABLE>(q0, table, t), s1 = 0.5f * eval_height<TABLE>(q1, table, t);
-            if (NF == 4 || (NF == 2 && fg == 0) || (NF == 1 && fg == 0)) {
-                pack_interior<0>(s0, kxA, kzA, q0.z, s1, kxB, kzA, q1.z, &a, &b);
-                put<0>(smem, 0, cp, eA, eB, a, b);
-            }
-            if (NF == 4 || (NF == 2 && fg == 0) || (NF == 1 && fg == 1)) {
-                pack_interior<1>(s0, kxA, kzA, q0.z, s1, kxB, kzA, q1.z, &a, &b);
-                put<1>(smem, NF == 1 ? 0 : 1, cp, eA, eB, a, b);
-            }
-            if (NF == 4 || (NF == 2 && fg == 1) || (NF == 1 && fg == 2)) {
-                pack_interior<2>(s0, kxA, kzA, q0.z, s1, kxB, kzA, q1.z, &a, &b);
-                put<2>(smem, NF == 4 ? 2 : 0, cp, eA, eB, a, b);
-            }
-            if (NF == 4 || (NF == 2 && fg == 1) || (NF == 1 && fg == 3)) {
-                pack_interior<3>(s0, kxA, kzA, q0.z, s1, kxB, kzA, q1.z, &a, &b);
-                put<3>(smem, NF == 4 ? 3 : (NF == 2 ? 1 : 0), cp, eA, eB, a, b);
-            }
-        } else {
-            const float4 q0 = td.h0[nA * N + mA], q1 = td.h0[nB * N + mA];
-            const float4 q2 = td.h0[nA * N + mB], q3 = td.h0[nB * N + mB];
-            const float h0 = eval_height<TABLE>(q0, table, t), h1 = eval_height<TABLE>(q1, table, t);
-            const float h2 = eval_height<TABLE>(q2, table, t), h3 = eval_height<TABLE>(q3, table, t);
-            const int mask = ((i != 0) ? 2 : 0) | ((j != 0) ? 1 : 0);
-            Point pt[4];
-            pt[0] = Point{h0, kxA, kzA, rmul(kxA, q0.z), rmul(kzA, q0.z)};
-            pt[1] = Point{h1, kxB, kzA, rmul(kxB, q1.z), rmul(kzA, q1.z)};
-            pt[2] = Point{h2, kxA, kzB, rmul(kxA, q2.z), rmul(kzB, q2.z)};
-            pt[3] = Point{h3, kxB, kzB, rmul(kxB, q3.z), rmul(kzB, q3.z)};
-            if (NF == 4 || (NF == 2 && fg == 0) || (NF == 1 && fg == 0)) {
-                pack_general<0>(pt, mask, &a, &b);
-                put<0>(smem, 0, cp, eA, eB, a, b);
-            }
-            if (NF == 4 || (NF == 2 && fg == 0) || (NF == 1 && fg == 1)) {
-                pack_general<1>(pt, mask, &a, &b);
-                put<1>(smem, NF == 1 ? 0 : 1, cp, eA, eB, a, b);
-            }
-            if (NF == 4 || (NF == 2 && fg == 1) || (NF == 1 && fg == 2)) {
-                pack_general<2>(pt, mask, &a, &b);
-                put<2>(smem, NF == 4 ? 2 : 0, cp, eA, eB, a, b);
-            }
-            if (NF == 4 || (NF == 2 && fg == 1) || (NF == 1 && fg == 3)) {
-                pack_general<3>(pt, mask, &a, &b);
-                put<3>(smem, NF == 4 ? 3 : (NF == 2 ? 1 : 0), cp, eA, eB, a, b);
+        if (NF == 4 || (NF == 2 && fg == 0) || (NF == 1 && fg == 0)) {
+            pack_general<0>(pt, mask, &a, &b);
+            put<0>(smem, 0, cp, eA, eB, a, b);
+        }
+        if (NF == 4 || (NF == 2 && fg == 0) || (NF == 1 && fg == 1)) {
+            pack_general<1>(pt, mask, &a, &b);
+            put<1>(smem, NF == 1 ? 0 : 1, cp, eA, eB, a, b);
+        }
+        if (NF == 4 || (NF == 2 && fg == 1) || (NF == 1 && fg == 2)) {
+            pack_general<2>(pt, mask, &a, &b);
+            put<2>(smem, NF == 4 ? 2 : 0, cp, eA, eB, a, b);
+        }
+        if (NF == 4 || (NF == 2 && fg == 1) || (NF == 1 && fg == 3)) {
+            pack_general<3>(pt, mask, &a, &b);
+            put<3>(smem, NF == 4 ? 3 : (NF == 2 ? 1 : 0), cp, eA, eB, a, b);
+        }
+    }
+
+    // evolve phase of one thread: its row pairs i = i0, i0+IT, ... and column pairs cp = cg, cg+CG, ...
+    // Interior items read the pair-summed records; all records of a row pair are requested before any is
+    // used, so the L2 latency is paid once per row pair instead of once per item.
+    static constexpr int CPT = CP / CG;  // column pairs per thread
+    template <bool TABLE>
+    static WSO_HD void evolve_thread(const TileDev& td, const float2* table, float t, int fg, float2* smem, int bx,
+                                     int tid) {
+        const int i0 = tid % IT, cg = tid / IT;
+        for (int i = i0; i < H; i += IT) {
+            if (i != 0 && td.use_pairs) {
+                float4 q0[CPT], q1[CPT];
+#pragma unroll
+                for (int k = 0; k < CPT; ++k) {
+                    const int j = bx * CP + cg + k * CG;
+                    const float4* rec = td.hs + ((size_t)j * H + i) * 2;
+                    q0[k] = rec[0];
+                    q1[k] = rec[1];
+                }
+                const float kzA = td.kv[i];
+                const int eA = pad_idx(i), eB = pad_idx(N - i);
+#pragma unroll
+                for (int k = 0; k < CPT; ++k) {
+                    const int cp = cg + k * CG;
+                    const int j = bx * CP + cp;
+                    if (j != 0) {
+                        const float s0 = 0.5f * eval_height<TABLE>(q0[k], table, t);
+                        const float s1 = 0.5f * eval_height<TABLE>(q1[k], table, t);
+                        pack_interior_item(smem, fg, cp, eA, eB, s0, s1, td.kv[j], td.kv[N - j], kzA, q0[k].z, q1[k].z);
+                    } else {
+                        evolve_item_general<TABLE>(td, table, t, fg, smem, cp, i, j);
+                    }
+                }
+            } else {
+                for (int cp = cg; cp < CP; cp += CG) evolve_item_general<TABLE>(td, table, t, fg, smem, cp, i, bx * CP + cp);
             }
         }
     }
@@ -263,19 +302,22 @@ struct Pass1 {
         }
 
         // ---- evolve: 4 wave vectors per work item, all NF fields ------------------------------------
+#ifndef WSO_EXP_SKIP_EVOLVE
         ex.each([&](int tid, ThreadState&) {
-            const int i0 = tid % IT, cg = tid / IT;
-            for (int i = i0; i < H; i += IT)
-                for (int cp = cg; cp < CP; cp += CG) {
-                    if (use_table) evolve_item<true>(td, table, t, by, smem, cp, i, bx * CP + cp);
-                    else evolve_item<false>(td, table, t, by, smem, cp, i, bx * CP + cp);
-                }
+            if (use_table) evolve_thread<true>(td, table, t, by, smem, bx, tid);
+            else evolve_thread<false>(td, table, t, by, smem, bx, tid);
         });
+#endif
         ex.sync();
 
         // ---- B complex FFTs of length N along m ---------------------------------------------------
+#ifndef WSO_EXP_SKIP_FFT1
         RunStages<LOGN, B, 0, 1, Exec>::run(ex, smem, args.tw);
+#endif
         ex.sync();  // the split below reads CP lines per work item
+#ifdef WSO_EXP_SKIP_STORE1
+        if (args.W != nullptr) return;
+#endif
 
         // ---- split the two real columns, keep m' in [0, N/2), store W[m'][f][slot] ---------------
         // thread -> fixed column pair cp = tid % CP (CP adjacent slots = one 8*CP-byte segment per m'),
