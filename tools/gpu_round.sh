@@ -1,0 +1,24 @@
+#!/bin/bash
+# Dev tool: one gpurun call = GPU parity tests + smoke + bench (c2 and friends) + ncu launch list + ncu full capture.
+# usage (under gpurun): bash tools/gpu_round.sh TAG [quick]
+TAG=${1:-r1}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/smi.txt 2>&1
+nproc > $OUT/host.txt; grep -m1 'model name' /proc/cpuinfo >> $OUT/host.txt; free -g | head -2 >> $OUT/host.txt
+timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_gpu.log
+timeout 300 python __graft_entry__.py smoke > $OUT/smoke.log 2>&1; echo "smoke rc=$?" | tee -a $OUT/smoke.log
+for wl in c2 c1 c3 c4; do
+  extra="--no-cpu-baseline"; [ $wl = c2 ] && extra=""
+  timeout 600 python bench.py --workload $wl $extra > $OUT/bench_$wl.json 2> $OUT/bench_$wl.err; echo "bench $wl rc=$?"
+done
+timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref_c2.json 2> $OUT/bench_ref_c2.err
+if [ "$2" != quick ]; then
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_c2.csv \
+     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/ncu_launch_bench.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:wso_ -s 30 -c 6 -o $OUT/prof_c2 \
+     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/ncu_full_c2.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:wso_ -s 12 -c 3 -o $OUT/prof_c3 \
+     python bench.py --workload c3 --steps 2 --warmup 3 --no-cpu-baseline > $OUT/ncu_full_c3.log 2>&1
+fi
+tail -3 $OUT/pytest_gpu.log; cat $OUT/bench_c2.json | cut -c1-1500
