@@ -66,7 +66,7 @@ static int run_cfg(const float* amp_t, const float* omega_t, const float* kv, fl
     std::vector<float2> W((size_t)H * 4 * N);
     LaunchArgs args;
     std::memset(&args, 0, sizeof(args));
-    args.tiles = &td;
+    args.td[0] = td;
     args.tw = tw.data();
     args.W = W.data();
     args.disp = reinterpret_cast<float4*>(disp);

@@ -12,6 +12,8 @@ for wl in c2 c1 c3 c4; do
   extra="--no-cpu-baseline"; [ $wl = c2 ] && extra=""
   timeout 600 python bench.py --workload $wl $extra > $OUT/bench_$wl.json 2> $OUT/bench_$wl.err; echo "bench $wl rc=$?"
 done
+for n in 512 1024; do timeout 120 tools/lat_bench $n 2000 >> $OUT/lat_bench.jsonl 2>> $OUT/lat_bench.err; done
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 90 --csv --log-file $OUT/launches_lat512.csv tools/lat_bench 512 20 > /dev/null 2>&1
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref_c2.json 2> $OUT/bench_ref_c2.err
 if [ "$2" != quick ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_c2.csv \
@@ -21,4 +23,4 @@ if [ "$2" != quick ]; then
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:wso_ -s 12 -c 3 -o $OUT/prof_c3 \
      python bench.py --workload c3 --steps 2 --warmup 3 --no-cpu-baseline > $OUT/ncu_full_c3.log 2>&1
 fi
-tail -3 $OUT/pytest_gpu.log; cat $OUT/bench_c2.json | cut -c1-1500
+tail -3 $OUT/pytest_gpu.log; cat $OUT/lat_bench.jsonl; python tools/summ.py $OUT/bench_c?.json; cat $OUT/bench_c2.json | cut -c1-1500

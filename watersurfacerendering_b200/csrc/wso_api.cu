@@ -51,7 +51,6 @@ struct wso_ctx {
     float4* d_h0 = nullptr;      // [tile][n][m] (amp.re, amp.im, 1/|k|, omega or j)
     float4* d_hs = nullptr;      // [tile][j][i][2] pair-summed records (see TileDev::hs)
     float* d_kv = nullptr;       // [tile][N]
-    TileDev* d_tiles = nullptr;  // [tile]
     float2* d_tw = nullptr;      // [N]
     float2* d_W = nullptr;       // [2][chunk][N/2][4][N]  (double buffered across chunks)
     float4* d_disp = nullptr;    // [slot][N*N]
@@ -118,7 +117,6 @@ void free_device_buffers(wso_ctx* c) {
     cudaFree(c->d_h0); c->d_h0 = nullptr;
     cudaFree(c->d_hs); c->d_hs = nullptr;
     cudaFree(c->d_kv); c->d_kv = nullptr;
-    cudaFree(c->d_tiles); c->d_tiles = nullptr;
     cudaFree(c->d_tw); c->d_tw = nullptr;
     cudaFree(c->d_W); c->d_W = nullptr;
     cudaFree(c->d_disp); c->d_disp = nullptr;
@@ -157,7 +155,6 @@ int allocate_for_size(wso_ctx* c, uint32_t n) {
     WSO_CUDA(c, cudaMalloc(&c->d_h0, sizeof(float4) * n2 * c->max_tiles));
     WSO_CUDA(c, cudaMalloc(&c->d_hs, sizeof(float4) * (n2 / 2) * c->max_tiles));
     WSO_CUDA(c, cudaMalloc(&c->d_kv, sizeof(float) * n * c->max_tiles));
-    WSO_CUDA(c, cudaMalloc(&c->d_tiles, sizeof(TileDev) * c->max_tiles));
     WSO_CUDA(c, cudaMalloc(&c->d_tw, sizeof(float2) * n));
     WSO_CUDA(c, cudaMalloc(&c->d_W, w_item * chunk * 2));
     WSO_CUDA(c, cudaMalloc(&c->d_disp, sizeof(float4) * n2 * c->max_slots));
@@ -190,8 +187,6 @@ int allocate_for_size(wso_ctx* c, uint32_t n) {
         c->tiles[t].is_prepared = false;
         c->tiles[t].h0.clear();
     }
-    WSO_CUDA(c, cudaMemcpyAsync(c->d_tiles, c->h_tiles.data(), sizeof(TileDev) * c->max_tiles,
-                                cudaMemcpyHostToDevice, c->stream));
     WSO_CUDA(c, cudaStreamSynchronize(c->stream));
     return WSO_OK;
 }
@@ -254,7 +249,6 @@ int upload_h0(wso_ctx* c, uint32_t tile, const wso_h0_record* h0) {
     c->h_tiles[tile].omega0 = omega0;
     c->h_tiles[tile].table_len = table_ok ? jmax + 1 : 0;
     c->h_tiles[tile].use_pairs = pairs_ok ? 1 : 0;
-    WSO_CUDA(c, cudaMemcpy(c->d_tiles + tile, &c->h_tiles[tile], sizeof(TileDev), cudaMemcpyHostToDevice));
     Tile& tl = c->tiles[tile];
     if (tl.h0.data() != h0) tl.h0.assign(h0, h0 + n2);
     tl.prepared = tl.params;
@@ -262,16 +256,10 @@ int upload_h0(wso_ctx* c, uint32_t tile, const wso_h0_record* h0) {
     return WSO_OK;
 }
 
+// lambda takes effect at the next compute without a Prepare (reference: SetLambda, WSTessendorf.h:181); the tile
+// constants travel by value with every launch, so refreshing the host copy is all there is to do
 int push_lambdas(wso_ctx* c) {
-    bool dirty = false;
-    for (uint32_t t = 0; t < c->max_tiles; ++t)
-        if (c->h_tiles[t].lambda != c->tiles[t].params.lambda) {
-            c->h_tiles[t].lambda = c->tiles[t].params.lambda;
-            dirty = true;
-        }
-    if (dirty)
-        WSO_CUDA(c, cudaMemcpyAsync(c->d_tiles, c->h_tiles.data(), sizeof(TileDev) * c->max_tiles,
-                                    cudaMemcpyHostToDevice, c->stream));
+    for (uint32_t t = 0; t < c->max_tiles; ++t) c->h_tiles[t].lambda = c->tiles[t].params.lambda;
     return WSO_OK;
 }
 
@@ -290,7 +278,6 @@ int begin_prepare(wso_ctx* c, uint32_t tile) {
 int enqueue_chunk(wso_ctx* c, uint32_t n_items, const uint32_t* tiles, const float* t, uint32_t first_slot,
                   int wbuf, cudaStream_t stream) {
     LaunchArgs args;
-    args.tiles = c->d_tiles;
     args.tw = c->d_tw;
     args.W = c->d_W + (size_t)wbuf * c->chunk * ((size_t)c->n * c->n * 2);
     args.disp = c->d_disp;
@@ -301,8 +288,12 @@ int enqueue_chunk(wso_ctx* c, uint32_t n_items, const uint32_t* tiles, const flo
         args.items[i].tile = tiles ? tiles[i] : 0u;
         args.items[i].slot = first_slot + i;
         args.items[i].t = t[i];
+        args.td[i] = c->h_tiles[args.items[i].tile];
     }
-    for (uint32_t i = n_items; i < (uint32_t)wso::kMaxChunk; ++i) args.items[i] = BatchItem{0u, 0u, 0.0f};
+    for (uint32_t i = n_items; i < (uint32_t)wso::kMaxChunk; ++i) {
+        args.items[i] = BatchItem{0u, 0u, 0.0f};
+        args.td[i] = TileDev{};
+    }
     cudaEvent_t* ev = nullptr;
     if (c->profiling) {
         if (c->prof_used + 4 > c->prof_events.size()) {

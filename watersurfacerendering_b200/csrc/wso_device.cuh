@@ -194,6 +194,13 @@ struct DeviceExec {
     }
     __device__ __forceinline__ void sync() { __syncthreads(); }
 
+    // Programmatic dependent launch (the launches carry cudaLaunchAttributeProgrammaticStreamSerialization).
+    // pdl_wait(): block until the preceding kernel of the stream has completed and its writes are visible.
+    // pdl_release(): let the NEXT kernel of the stream start being scheduled.  Every kernel releases only after its
+    // own wait, so when a kernel starts, everything up to its predecessor's predecessor is complete.
+    __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+    __device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
     // Barrier over the G consecutive threads [g*G, (g+1)*G) that share one FFT line (or line pair), instead of
     // the whole CTA: lines are independent between the evolve / split / pack phases, so a CTA-wide barrier per
     // stage would only make 16 warps wait for the slowest one.  G <= 32: the group lives inside one warp;
@@ -242,6 +249,8 @@ struct HostExec {
         for (int t = 0; t < nthreads; ++t) f(t, states[t]);
     }
     void sync() {}
+    void pdl_wait() {}
+    void pdl_release() {}
     template <int G, int T>
     void sync_group(int) {}
     void commit_minmax(float* out) {

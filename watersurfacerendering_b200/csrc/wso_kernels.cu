@@ -1,105 +1,181 @@
 // wso_kernels.cu — __global__ entry points and launch dispatch for sm_100a.
 #include "wso_launch.h"
 
+#include <type_traits>
+
 #include "wso_kernels.cuh"
 
 namespace wso {
 
-// CTA tiling per tile size.  CP: column pairs per K1 CTA, NF: packed fields per K1 CTA,
-// RI: row items (each = output rows m' and N-m') per K2 CTA.  CTA threads = lines * N / 16.
+// CTA tiling.  CP: column pairs per K1 CTA, NF: packed fields per K1 CTA, RI: row items (each = output rows m'
+// and N-m') per K2 CTA, RH: row items per K2h CTA (one line each).  CTA threads = lines * N / 16.
+template <int CP_, int NF_, int RI_, int RH_>
+struct Tiling {
+    static constexpr int CP = CP_, NF = NF_, RI = RI_, RH = RH_;
+};
+// Two tilings per tile size:
+//   Bulk - batched launches (many tile-frames per launch): larger CTAs, 32-byte W store segments; tuned with
+//          tools/sweep_build.py + tools/sweep_run.sh on B200 (profiles/r1b_sweep.md)
+//   Lat  - a launch with few tile-frames (the reference's one ComputeWaves(t) per frame): small CTAs so that a single
+//          512^2 or 1024^2 tile still spreads over all 148 SMs
 template <int LOGN> struct Cfg;
-// RH: row items per K2h CTA (one line each).
-template <> struct Cfg<4>  { static constexpr int CP = 8, NF = 4, RI = 8, RH = 8; };
-template <> struct Cfg<5>  { static constexpr int CP = 8, NF = 4, RI = 8, RH = 16; };
-template <> struct Cfg<6>  { static constexpr int CP = 8, NF = 4, RI = 8, RH = 16; };
-template <> struct Cfg<7>  { static constexpr int CP = 4, NF = 4, RI = 8, RH = 16; };
-template <> struct Cfg<8>  { static constexpr int CP = 4, NF = 4, RI = 4, RH = 8; };
+template <> struct Cfg<4>  { using Bulk = Tiling<8, 4, 8, 8>;   using Lat = Tiling<2, 4, 2, 4>; };
+template <> struct Cfg<5>  { using Bulk = Tiling<8, 4, 8, 16>;  using Lat = Tiling<2, 4, 2, 4>; };
+template <> struct Cfg<6>  { using Bulk = Tiling<8, 4, 8, 16>;  using Lat = Tiling<2, 4, 2, 4>; };
+template <> struct Cfg<7>  { using Bulk = Tiling<4, 4, 8, 16>;  using Lat = Tiling<2, 4, 2, 4>; };
+template <> struct Cfg<8>  { using Bulk = Tiling<4, 4, 4, 8>;   using Lat = Tiling<2, 2, 1, 2>; };
 // (the WSO_TUNE_* macros exist for tuning sweeps: tools/tune_build.sh builds variant libraries)
 #ifndef WSO_TUNE_CP9
 #define WSO_TUNE_CP9 4
 #define WSO_TUNE_NF9 4
-#define WSO_TUNE_RI9 4
-#define WSO_TUNE_RH9 8
+#define WSO_TUNE_RI9 1
+#define WSO_TUNE_RH9 4
 #endif
 #ifndef WSO_TUNE_CP10
 #define WSO_TUNE_CP10 4
 #define WSO_TUNE_NF10 2
-#define WSO_TUNE_RI10 4
+#define WSO_TUNE_RI10 2
 #define WSO_TUNE_RH10 8
 #endif
 #ifndef WSO_TUNE_CP11
 #define WSO_TUNE_CP11 4
-#define WSO_TUNE_NF11 2
-#define WSO_TUNE_RI11 2
-#define WSO_TUNE_RH11 4
+#define WSO_TUNE_NF11 1
+#define WSO_TUNE_RI11 1
+#define WSO_TUNE_RH11 2
 #endif
-template <> struct Cfg<9>  { static constexpr int CP = WSO_TUNE_CP9, NF = WSO_TUNE_NF9, RI = WSO_TUNE_RI9, RH = WSO_TUNE_RH9; };
-template <> struct Cfg<10> { static constexpr int CP = WSO_TUNE_CP10, NF = WSO_TUNE_NF10, RI = WSO_TUNE_RI10, RH = WSO_TUNE_RH10; };
-template <> struct Cfg<11> { static constexpr int CP = WSO_TUNE_CP11, NF = WSO_TUNE_NF11, RI = WSO_TUNE_RI11, RH = WSO_TUNE_RH11; };
-template <> struct Cfg<12> { static constexpr int CP = 4, NF = 1, RI = 2, RH = 4; };
-template <> struct Cfg<13> { static constexpr int CP = 2, NF = 1, RI = 1, RH = 2; };
+#ifndef WSO_TUNE_LCP9
+#define WSO_TUNE_LCP9 2
+#define WSO_TUNE_LNF9 2
+#define WSO_TUNE_LRI9 1
+#define WSO_TUNE_LRH9 2
+#endif
+#ifndef WSO_TUNE_LCP10
+#define WSO_TUNE_LCP10 2
+#define WSO_TUNE_LNF10 2
+#define WSO_TUNE_LRI10 1
+#define WSO_TUNE_LRH10 2
+#endif
+template <> struct Cfg<9> {
+    using Bulk = Tiling<WSO_TUNE_CP9, WSO_TUNE_NF9, WSO_TUNE_RI9, WSO_TUNE_RH9>;
+    using Lat = Tiling<WSO_TUNE_LCP9, WSO_TUNE_LNF9, WSO_TUNE_LRI9, WSO_TUNE_LRH9>;
+};
+template <> struct Cfg<10> {
+    using Bulk = Tiling<WSO_TUNE_CP10, WSO_TUNE_NF10, WSO_TUNE_RI10, WSO_TUNE_RH10>;
+    using Lat = Tiling<WSO_TUNE_LCP10, WSO_TUNE_LNF10, WSO_TUNE_LRI10, WSO_TUNE_LRH10>;
+};
+template <> struct Cfg<11> {
+    using Bulk = Tiling<WSO_TUNE_CP11, WSO_TUNE_NF11, WSO_TUNE_RI11, WSO_TUNE_RH11>;
+    using Lat = Bulk;
+};
+template <> struct Cfg<12> { using Bulk = Tiling<4, 1, 2, 4>; using Lat = Bulk; };
+template <> struct Cfg<13> { using Bulk = Tiling<2, 1, 1, 2>; using Lat = Bulk; };
 
 // 1024 resident threads per SM at <= 64 registers: every thread carries 16 complex values between barriers
 constexpr int min_blocks(int threads) { return threads >= 1024 ? 1 : (1024 / threads > 8 ? 8 : 1024 / threads); }
 
-template <int LOGN>
-__global__ void __launch_bounds__(Pass1<LOGN, Cfg<LOGN>::CP, Cfg<LOGN>::NF>::T,
-                                  min_blocks(Pass1<LOGN, Cfg<LOGN>::CP, Cfg<LOGN>::NF>::T))
-wso_pass1_kernel(const __grid_constant__ LaunchArgs args) {
+template <int LOGN, class TL, class Args>
+__global__ void __launch_bounds__(Pass1<LOGN, TL::CP, TL::NF>::T, min_blocks(Pass1<LOGN, TL::CP, TL::NF>::T))
+wso_pass1_kernel(const __grid_constant__ Args args) {
     extern __shared__ __align__(16) float2 smem[];
     DeviceExec ex;
-    Pass1<LOGN, Cfg<LOGN>::CP, Cfg<LOGN>::NF>::run(ex, smem, blockIdx.x, blockIdx.y, blockIdx.z, args);
+    Pass1<LOGN, TL::CP, TL::NF>::run(ex, smem, blockIdx.x, blockIdx.y, blockIdx.z, args);
 }
 
-template <int LOGN>
-__global__ void __launch_bounds__(Pass2<LOGN, Cfg<LOGN>::RI, false>::T, min_blocks(Pass2<LOGN, Cfg<LOGN>::RI, false>::T))
-wso_pass2_kernel(const __grid_constant__ LaunchArgs args) {
+template <int LOGN, class TL, class Args>
+__global__ void __launch_bounds__(Pass2<LOGN, TL::RI, false>::T, min_blocks(Pass2<LOGN, TL::RI, false>::T))
+wso_pass2_kernel(const __grid_constant__ Args args) {
     extern __shared__ __align__(16) float2 smem[];
     DeviceExec ex;
-    Pass2<LOGN, Cfg<LOGN>::RI, false>::run(ex, smem, blockIdx.x, blockIdx.y, blockIdx.z, args);
+    Pass2<LOGN, TL::RI, false>::run(ex, smem, blockIdx.x, blockIdx.y, blockIdx.z, args);
 }
 
 // K2h: height extrema (min/max -> amplitude A) ahead of K2, so that K2 writes disp.y already normalised and no
 // second pass over the displacement map is needed (reference: the serial NormalizeHeights sweep, WSTessendorf.cpp:443-455)
-template <int LOGN>
-__global__ void __launch_bounds__(Pass2<LOGN, Cfg<LOGN>::RH, true>::T, min_blocks(Pass2<LOGN, Cfg<LOGN>::RH, true>::T))
-wso_heights_kernel(const __grid_constant__ LaunchArgs args) {
+template <int LOGN, class TL, class Args>
+__global__ void __launch_bounds__(Pass2<LOGN, TL::RH, true>::T, min_blocks(Pass2<LOGN, TL::RH, true>::T))
+wso_heights_kernel(const __grid_constant__ Args args) {
     extern __shared__ __align__(16) float2 smem[];
     DeviceExec ex;
-    Pass2<LOGN, Cfg<LOGN>::RH, true>::run(ex, smem, blockIdx.x, 0, blockIdx.z, args);
+    Pass2<LOGN, TL::RH, true>::run(ex, smem, blockIdx.x, 0, blockIdx.z, args);
+}
+
+// Every launch carries the programmatic-stream-serialization attribute: the next kernel of the stream is
+// scheduled while this one drains and blocks in griddepcontrol.wait (pdl_wait() at the top of each kernel body)
+// until its predecessor has completed and flushed - stream order is preserved, launch latency is hidden.
+template <class Args, class Kern>
+static cudaError_t launch_pdl(Kern kern, dim3 grid, int threads, int smem, cudaStream_t stream, const Args& args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3((unsigned)threads, 1, 1);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, args);
+}
+
+template <int LOGN, class TL, class Args>
+static cudaError_t launch_tiled(const Args& args, int n_items, cudaStream_t stream, cudaEvent_t* ev) {
+    using P1 = Pass1<LOGN, TL::CP, TL::NF>;
+    using P2 = Pass2<LOGN, TL::RI, false>;
+    using PH = Pass2<LOGN, TL::RH, true>;
+    static bool configured[16] = {};  // per device: opt in to > 48 KB of dynamic shared memory once
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 16 || !configured[dev]) {
+        cudaError_t e;
+        e = cudaFuncSetAttribute(wso_pass1_kernel<LOGN, TL, Args>, cudaFuncAttributeMaxDynamicSharedMemorySize, P1::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(wso_pass2_kernel<LOGN, TL, Args>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(wso_heights_kernel<LOGN, TL, Args>, cudaFuncAttributeMaxDynamicSharedMemorySize, PH::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 16) configured[dev] = true;
+    }
+    cudaError_t e;
+    if (ev) cudaEventRecord(ev[0], stream);
+    const dim3 g1(P1::H / TL::CP, 4 / TL::NF, n_items);
+    e = launch_pdl(wso_pass1_kernel<LOGN, TL, Args>, g1, P1::T, P1::SMEM_BYTES, stream, args);
+    if (e != cudaSuccess) return e;
+    if (ev) cudaEventRecord(ev[1], stream);
+    const dim3 gh(PH::H / TL::RH, 1, n_items);
+    e = launch_pdl(wso_heights_kernel<LOGN, TL, Args>, gh, PH::T, PH::SMEM_BYTES, stream, args);
+    if (e != cudaSuccess) return e;
+    if (ev) cudaEventRecord(ev[2], stream);
+    const dim3 g2(P2::H / TL::RI, 2, n_items);
+    e = launch_pdl(wso_pass2_kernel<LOGN, TL, Args>, g2, P2::T, P2::SMEM_BYTES, stream, args);
+    if (e != cudaSuccess) return e;
+    if (ev) cudaEventRecord(ev[3], stream);
+    return cudaGetLastError();
 }
 
 template <int LOGN>
-static cudaError_t launch_all(const LaunchArgs& args, int n_items, cudaStream_t stream, bool first_use,
-                              cudaEvent_t* ev) {
-    using P1 = Pass1<LOGN, Cfg<LOGN>::CP, Cfg<LOGN>::NF>;
-    using P2 = Pass2<LOGN, Cfg<LOGN>::RI, false>;
-    using PH = Pass2<LOGN, Cfg<LOGN>::RH, true>;
-    if (first_use) {
-        cudaError_t e;
-        e = cudaFuncSetAttribute(wso_pass1_kernel<LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, P1::SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(wso_pass2_kernel<LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2::SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(wso_heights_kernel<LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, PH::SMEM_BYTES);
-        if (e != cudaSuccess) return e;
+static cudaError_t launch_all(const LaunchArgs& args, int n_items, cudaStream_t stream, bool, cudaEvent_t* ev) {
+    using B = typename Cfg<LOGN>::Bulk;
+    using L = typename Cfg<LOGN>::Lat;
+    // few tile-frames in this launch: the Bulk grid of K1 would leave SMs idle -> fine-grained tiling and the
+    // small parameter block
+    constexpr int bulk_ctas_per_item = ((1 << LOGN) / 2 / B::CP) * (4 / B::NF);
+    if (n_items <= kSmallChunk && n_items * bulk_ctas_per_item < 2 * 148) {
+        LaunchArgsSmall sm;
+        sm.tw = args.tw; sm.W = args.W; sm.disp = args.disp; sm.norm = args.norm;
+        sm.minmax = args.minmax; sm.amp_out = args.amp_out;
+        for (int i = 0; i < kSmallChunk; ++i) { sm.items[i] = args.items[i]; sm.td[i] = args.td[i]; }
+        return launch_tiled<LOGN, L, LaunchArgsSmall>(sm, n_items, stream, ev);
     }
-    if (ev) cudaEventRecord(ev[0], stream);
-    const dim3 g1(P1::H / Cfg<LOGN>::CP, 4 / Cfg<LOGN>::NF, n_items);
-    wso_pass1_kernel<LOGN><<<g1, P1::T, P1::SMEM_BYTES, stream>>>(args);
-    if (ev) cudaEventRecord(ev[1], stream);
-    const dim3 gh(PH::H / Cfg<LOGN>::RH, 1, n_items);
-    wso_heights_kernel<LOGN><<<gh, PH::T, PH::SMEM_BYTES, stream>>>(args);
-    if (ev) cudaEventRecord(ev[2], stream);
-    const dim3 g2(P2::H / Cfg<LOGN>::RI, 2, n_items);
-    wso_pass2_kernel<LOGN><<<g2, P2::T, P2::SMEM_BYTES, stream>>>(args);
-    if (ev) cudaEventRecord(ev[3], stream);
-    return cudaGetLastError();
+    return launch_tiled<LOGN, B, LaunchArgs>(args, n_items, stream, ev);
 }
 
 cudaError_t launch_compute_waves(int logn, const LaunchArgs& args, int n_items, cudaStream_t stream,
                                  bool first_use, cudaEvent_t* ev) {
     switch (logn) {
+// WSO_ONLY_LOGN: tuning builds instantiate a single size (tools/tune_build.sh) to keep compile times short
+#ifdef WSO_ONLY_LOGN
+        case WSO_ONLY_LOGN: return launch_all<WSO_ONLY_LOGN>(args, n_items, stream, first_use, ev);
+#else
         case 4: return launch_all<4>(args, n_items, stream, first_use, ev);
         case 5: return launch_all<5>(args, n_items, stream, first_use, ev);
         case 6: return launch_all<6>(args, n_items, stream, first_use, ev);
@@ -110,6 +186,7 @@ cudaError_t launch_compute_waves(int logn, const LaunchArgs& args, int n_items, 
         case 11: return launch_all<11>(args, n_items, stream, first_use, ev);
         case 12: return launch_all<12>(args, n_items, stream, first_use, ev);
         case 13: return launch_all<13>(args, n_items, stream, first_use, ev);
+#endif
         default: return cudaErrorInvalidValue;
     }
 }

@@ -40,21 +40,30 @@ struct TileDev {
 };
 
 struct BatchItem {
-    uint32_t tile;  // which h0 / parameter set
+    uint32_t tile;  // which h0 / parameter set (host bookkeeping; the kernels read td[] below)
     uint32_t slot;  // which output map slot
     float t;        // time
 };
 
-struct LaunchArgs {
-    const TileDev* tiles;  // device array
+// CAP: item capacity of the parameter block.  Batched launches use kMaxChunk; a launch of a few tile-frames uses
+// a small block (kernel parameters are copied into the command stream at every launch).
+template <int CAP>
+struct LaunchArgsT {
+    static constexpr int kCap = CAP;
     const float2* tw;      // [N] exp(+2*pi*i*k/N)
     float2* W;             // chunk scratch: [item][N/2][4][N]
     float4* disp;          // [slot][N*N]
     float4* norm;          // [slot][N*N]
     float* minmax;         // [slot][2]
     float* amp_out;        // [slot] amplitude A
-    BatchItem items[kMaxChunk];
+    BatchItem items[CAP];
+    // the tile constants of every item travel by value in the kernel parameters (constant bank): no dependent
+    // global load sits between CTA start and the first h0 request
+    TileDev td[CAP];
 };
+using LaunchArgs = LaunchArgsT<kMaxChunk>;
+static constexpr int kSmallChunk = 4;
+using LaunchArgsSmall = LaunchArgsT<kSmallChunk>;
 
 // reference: WSTessendorf.cpp:289-290 — max starts at FLT_MIN (smallest positive), min at FLT_MAX
 static constexpr float kInitMax = 1.17549435e-38f;
@@ -240,52 +249,52 @@ struct Pass1 {
     static WSO_HD void evolve_thread(const TileDev& td, const float2* table, float t, int fg, float2* smem, int bx,
                                      int tid) {
         const int i0 = tid % IT, cg = tid / IT;
-        for (int i = i0; i < H; i += IT) {
-            if (i != 0 && td.use_pairs) {
-                float4 q0[CPT], q1[CPT];
-#pragma unroll
-                for (int k = 0; k < CPT; ++k) {
-                    const int j = bx * CP + cg + k * CG;
-                    const float4* rec = td.hs + ((size_t)j * H + i) * 2;
-                    q0[k] = rec[0];
-                    q1[k] = rec[1];
-                }
-                const float kzA = td.kv[i];
-                const int eA = pad_idx(i), eB = pad_idx(N - i);
-#pragma unroll
-                for (int k = 0; k < CPT; ++k) {
-                    const int cp = cg + k * CG;
-                    const int j = bx * CP + cp;
-                    if (j != 0) {
-                        const float s0 = 0.5f * eval_height<TABLE>(q0[k], table, t);
-                        const float s1 = 0.5f * eval_height<TABLE>(q1[k], table, t);
-                        pack_interior_item(smem, fg, cp, eA, eB, s0, s1, td.kv[j], td.kv[N - j], kzA, q0[k].z, q1[k].z);
-                    } else {
-                        evolve_item_general<TABLE>(td, table, t, fg, smem, cp, i, j);
-                    }
-                }
-            } else {
+        if (!td.use_pairs) {  // foreign h0 (omega(k) != omega(-k)): every item through the per-point records
+            for (int i = i0; i < H; i += IT)
                 for (int cp = cg; cp < CP; cp += CG) evolve_item_general<TABLE>(td, table, t, fg, smem, cp, i, bx * CP + cp);
+            return;
+        }
+        // The row pair i = 0 (rows 0 and N/2, their own mirrors) needs the general path: four dependent record
+        // requests per item.  Its CP items are dealt to the last lanes of CP different warps so that they overlap
+        // instead of serialising in the one thread that owns i0 == 0.
+        if (T >= 32 * CP) {
+            if ((tid & 31) == 31 && (tid >> 5) < CP) evolve_item_general<TABLE>(td, table, t, fg, smem, tid >> 5, 0, bx * CP + (tid >> 5));
+        } else if (tid < CP) {
+            evolve_item_general<TABLE>(td, table, t, fg, smem, tid, 0, bx * CP + tid);
+        }
+        for (int i = i0; i < H; i += IT) {
+            if (i == 0) continue;
+            float4 q0[CPT], q1[CPT];
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) {
+                const int j = bx * CP + cg + k * CG;
+                const float4* rec = td.hs + ((size_t)j * H + i) * 2;
+                q0[k] = rec[0];
+                q1[k] = rec[1];
+            }
+            const float kzA = td.kv[i];
+            const int eA = pad_idx(i), eB = pad_idx(N - i);
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) {
+                const int cp = cg + k * CG;
+                const int j = bx * CP + cp;
+                if (j != 0) {
+                    const float s0 = 0.5f * eval_height<TABLE>(q0[k], table, t);
+                    const float s1 = 0.5f * eval_height<TABLE>(q1[k], table, t);
+                    pack_interior_item(smem, fg, cp, eA, eB, s0, s1, td.kv[j], td.kv[N - j], kzA, q0[k].z, q1[k].z);
+                } else {
+                    evolve_item_general<TABLE>(td, table, t, fg, smem, cp, i, j);
+                }
             }
         }
     }
 
     // bx: column-pair group, by: field group, bz: item within the chunk
-    template <class Exec>
-    static WSO_HD void run(Exec& ex, float2* smem, int bx, int by, int bz, const LaunchArgs& args) {
+    template <class Exec, class Args>
+    static WSO_HD void run(Exec& ex, float2* smem, int bx, int by, int bz, const Args& args) {
         const BatchItem item = args.items[bz];
-        const TileDev td = args.tiles[item.tile];
+        const TileDev& td = args.td[bz];
         const float t = item.t;
-
-        // the height min/max accumulators of this item's slot are reset here, ahead of K2
-        if (bx == 0 && by == 0) {
-            ex.each([&](int tid, ThreadState&) {
-                if (tid == 0) {
-                    args.minmax[2 * item.slot + 0] = kInitMin;
-                    args.minmax[2 * item.slot + 1] = kInitMax;
-                }
-            });
-        }
 
         // ---- per-frame (cos,sin)(omega_j * t) table: omega takes few distinct values j*omega0 ------
         float2* table = smem + B * LS;
@@ -318,6 +327,19 @@ struct Pass1 {
 #ifdef WSO_EXP_SKIP_STORE1
         if (args.W != nullptr) return;
 #endif
+        // Everything above touched only per-tile constants and shared memory, so it may overlap the tail of the
+        // previous kernel in the stream (the previous tile-frame's K2, which still reads W and the slot's min/max).
+        ex.pdl_wait();
+        ex.pdl_release();
+        // the height min/max accumulators of this item's slot are reset here, ahead of K2h
+        if (bx == 0 && by == 0) {
+            ex.each([&](int tid, ThreadState&) {
+                if (tid == 0) {
+                    args.minmax[2 * item.slot + 0] = kInitMin;
+                    args.minmax[2 * item.slot + 1] = kInitMax;
+                }
+            });
+        }
 
         // ---- split the two real columns, keep m' in [0, N/2), store W[m'][f][slot] ---------------
         // thread -> fixed column pair cp = tid % CP (CP adjacent slots = one 8*CP-byte segment per m'),
@@ -380,10 +402,17 @@ struct Pass2 {
     static_assert(T >= 1 && T <= 1024, "bad CTA size");
     static_assert(H % RI == 0, "bad tiling");
 
-    template <class Exec>
-    static WSO_HD void run(Exec& ex, float2* smem, int bx, int by, int bz, const LaunchArgs& args) {
+    template <class Exec, class Args>
+    static WSO_HD void run(Exec& ex, float2* smem, int bx, int by, int bz, const Args& args) {
         const BatchItem item = args.items[bz];
         const float2* Wit = args.W + (size_t)bz * ((size_t)H * 4 * N);
+        // K2h consumes what K1 (its predecessor in the stream) wrote: wait first.  K2 is released by K2h only after
+        // K2h's own wait, i.e. K1 is complete when K2 starts: K2 transforms W right away and waits (for K2h's
+        // min/max) only before the pack phase.
+        if constexpr (HEIGHT_ONLY) {
+            ex.pdl_wait();
+            ex.pdl_release();
+        }
 
         // ---- first stage straight from global memory (W rows are contiguous) ---------------------
         {
@@ -439,7 +468,9 @@ struct Pass2 {
         } else {
             // ---- pack: each transformed line pair yields output rows m' and N-m' -----------------
             // reference: WSTessendorf.cpp:385-437 (sign, lambda, packing) and :443-455 (normalisation)
-            const float lambda = args.tiles[item.tile].lambda;
+            ex.pdl_wait();
+            ex.pdl_release();
+            const float lambda = args.td[bz].lambda;
             const float amp = amplitude_of(args.minmax[2 * item.slot], args.minmax[2 * item.slot + 1]);
             const float inv_amp = rdiv(1.0f, amp);
             if (bx == 0 && by == 0) {

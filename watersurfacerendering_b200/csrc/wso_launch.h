@@ -4,7 +4,9 @@
 
 namespace wso {
 
-struct LaunchArgs;
+template <int CAP>
+struct LaunchArgsT;
+using LaunchArgs = LaunchArgsT<64>;  // kMaxChunk (wso_kernels.cuh)
 
 static constexpr int kMinLogN = 4;   // 16
 static constexpr int kMaxLogN = 13;  // 8192 (single-CTA line transforms; larger grids: slab path)
