@@ -143,6 +143,50 @@ WSO_API int wso_get_stats(const wso_ctx* ctx, uint64_t* kernel_launches, uint32_
 WSO_API int wso_set_profiling(wso_ctx* ctx, int on);
 WSO_API int wso_get_profile(wso_ctx* ctx, double* kernel_ms3, uint64_t* launches, uint64_t* tile_frames);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Slab-decomposed path: ONE large grid (2048..16384 per side) spread over P = 1, 2, 4 or 8 devices, one process
+ * and one wso_slab per device (BASELINE.json configs[4]; no reference counterpart - the reference caps the tile at
+ * 1024^2, WaterSurfaceMesh.h:45-46 - the arithmetic is the same ComputeWaves, WSTessendorf.cpp:284-441).
+ * Rank r evolves and transforms (along m) the column pairs (n, N-n) for n in [r*N/2P, (r+1)*N/2P) and, after the
+ * exchange, transforms (along n) and packs the rows m' and N-m' for m' in the same range.  Per tile-frame:
+ *     wso_slab_pass1(t)  ->  exchange  ->  wso_slab_heights  ->  all-reduce (min, max)  ->  wso_slab_pass2
+ * The exchange is either (fused) done by pass1 itself, whose stores go straight into the owners' receive buffers
+ * through NVLink peer mappings (wso_slab_ipc_handle / wso_slab_open_peer / wso_slab_set_fused) followed by any
+ * inter-rank barrier, or (unfused) ONE all-to-all of the `world` equal blocks of the send buffer into the receive
+ * buffer, issued by the caller (e.g. torch.distributed.all_to_all_single over NCCL) on the slab's stream.
+ * The all-reduce (min over [0], max over [1] of the 2-float minmax buffer) is the caller's as well. */
+typedef struct wso_slab wso_slab;
+WSO_API int wso_slab_create(const wso_params* p, int device, uint32_t rank, uint32_t world, wso_slab** out);
+WSO_API int wso_slab_destroy(wso_slab* s);
+/* Spectrum of this rank's columns: from a full N*N array in the reference layout (small grids, tests), or generated
+ * in place from a counter-based Gaussian source (seed, m*N+n) with the reference's Phillips/dispersion arithmetic
+ * (WSTessendorf.cpp:105-148).  wso_counter_h0 evaluates the same records for rows [m0, m0+rows) - for checkers. */
+WSO_API int wso_slab_import_h0(wso_slab* s, const wso_h0_record* h0_full);
+WSO_API int wso_slab_prepare_counter(wso_slab* s, uint64_t seed);
+WSO_API int wso_counter_h0(const wso_params* p, uint64_t seed, uint32_t m0, uint32_t rows, wso_h0_record* out);
+WSO_API int wso_slab_set_lambda(wso_slab* s, float lambda);
+WSO_API int wso_slab_set_stream(wso_slab* s, void* cuda_stream);
+/* Exchange buffers: send/recv = `world` blocks of block_bytes each (block d of send goes to rank d; block r of recv
+ * came from rank r); minmax = 2 floats written by wso_slab_heights, to be all-reduced before wso_slab_pass2. */
+WSO_API int wso_slab_buffers(wso_slab* s, void** send, void** recv, size_t* block_bytes, void** minmax);
+/* Fused exchange: 64-byte CUDA IPC handle of this rank's receive buffer; map every peer's, then switch on. */
+WSO_API int wso_slab_ipc_handle(wso_slab* s, void* handle64);
+WSO_API int wso_slab_open_peer(wso_slab* s, uint32_t peer, const void* handle64);
+WSO_API int wso_slab_set_fused(wso_slab* s, int on);
+/* Use the two-CTA cluster variant of K2 (always used at 16384, where a line pair exceeds one SM's shared memory). */
+WSO_API int wso_slab_force_pair(wso_slab* s, int on);
+WSO_API int wso_slab_pass1(wso_slab* s, float t);
+WSO_API int wso_slab_heights(wso_slab* s);
+WSO_API int wso_slab_pass2(wso_slab* s);
+WSO_API int wso_slab_sync(wso_slab* s);
+WSO_API int wso_slab_read_heights(wso_slab* s, float* amplitude, float* min_height, float* max_height);
+/* Output: this rank's 2*N/2P rows of each map, N RGBA32F texels per row; wso_slab_row_index gives the global row
+ * of every local row (local row ml < N/2P is row m' = r*N/2P + ml, local row N/2P + ml its mirror N-m'; N/2 for m'=0). */
+WSO_API int wso_slab_map_device(wso_slab* s, int which, void** dptr, uint32_t* rows);
+WSO_API int wso_slab_copy_rows(wso_slab* s, int which, float* dst_host);
+WSO_API int wso_slab_row_index(const wso_slab* s, uint32_t* rows);
+WSO_API const char* wso_slab_last_error(const wso_slab* s);
+
 WSO_API const char* wso_last_error(const wso_ctx* ctx); /* ctx may be NULL: last create failure */
 WSO_API const char* wso_version(void);
 

@@ -26,6 +26,11 @@ def lib():
         L.wso_emu_compute.argtypes = [C.c_int, C.c_int, vp, vp, vp, C.c_float, C.c_float, C.c_float, vp, vp, vp, vp,
                                       vp]
         L.wso_emu_compute.restype = C.c_int
+        L.wso_emu_compute_slab.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_float, C.c_float, C.c_float, vp,
+                                           vp, vp, vp]
+        L.wso_emu_compute_slab.restype = C.c_int
+        L.wso_emu_slab_rank_phase.argtypes = [C.c_int] * 5 + [vp, vp, vp, C.c_float, C.c_float, C.c_float] + [vp] * 6
+        L.wso_emu_slab_rank_phase.restype = C.c_int
         _lib = L
     return _lib
 
@@ -52,3 +57,81 @@ def compute(n, tile_length, lam, h0_re, h0_im, omega, t, variant=0, want_w=False
     if rc != 0:
         raise ValueError(f"no emulated configuration for logn={logn} variant={variant}")
     return a[0], disp, norm, mm[0], mm[1], w
+
+
+def compute_slab(n, tile_length, lam, h0_re, h0_im, omega, t, world, variant=0, anim_period=200.0):
+    """Same as compute(), through the slab-decomposed kernels on `world` emulated devices (fused peer stores)."""
+    logn = int(np.log2(n))
+    shift = int(np.log2(world))
+    amp_t = np.ascontiguousarray(np.stack([h0_re.T, h0_im.T], axis=-1).astype(np.float32))
+    om_t = np.ascontiguousarray(omega.T.astype(np.float32))
+    idx = np.arange(n, dtype=np.float32)
+    kv = (np.pi * (np.float32(2) * idx - np.float32(n)).astype(np.float64)
+          / np.float64(np.float32(tile_length))).astype(np.float32)
+    disp = np.zeros((n, n, 4), np.float32)
+    norm = np.zeros((n, n, 4), np.float32)
+    mm = np.zeros(2, np.float32)
+    a = np.zeros(1, np.float32)
+    p = lambda x: x.ctypes.data_as(C.c_void_p)
+    omega0 = 0.0 if anim_period is None else float(
+        np.float32(np.float64(np.float32(2.0)) * np.pi / np.float64(np.float32(anim_period))))
+    rc = lib().wso_emu_compute_slab(logn, variant, shift, p(amp_t), p(om_t), p(kv), omega0, float(lam), float(t),
+                                    p(disp), p(norm), p(mm), p(a))
+    if rc != 0:
+        raise ValueError(f"no emulated slab configuration for logn={logn} variant={variant} world={world} (rc={rc})")
+    return a[0], disp, norm, mm[0], mm[1]
+
+
+class EmuSlabBackend:
+    """Drop-in for watersurfacerendering_b200.slab.SlabBackend whose phases run the emulated kernel bodies on the
+    CPU (unfused exchange only): lets the gloo tests exercise the real SlabOcean orchestration without a GPU."""
+
+    def __init__(self, n, tile_length, lam, h0_re, h0_im, omega, rank, world, variant=0, anim_period=200.0):
+        import torch
+        self.n, self.rank, self.world = n, rank, world
+        self.logn, self.shift, self.variant = int(np.log2(n)), int(np.log2(world)), variant
+        self.hl = n // 2 // world
+        self.lam = float(lam)
+        self.amp_t = np.ascontiguousarray(np.stack([h0_re.T, h0_im.T], axis=-1).astype(np.float32))
+        self.om_t = np.ascontiguousarray(omega.T.astype(np.float32))
+        idx = np.arange(n, dtype=np.float32)
+        self.kv = (np.pi * (np.float32(2) * idx - np.float32(n)).astype(np.float64)
+                   / np.float64(np.float32(tile_length))).astype(np.float32)
+        self.omega0 = float(np.float32(np.float64(np.float32(2.0)) * np.pi / np.float64(np.float32(anim_period))))
+        blk = self.hl * 4 * 2 * self.hl * 2  # floats per block
+        self.send = torch.zeros(blk * world, dtype=torch.float32)
+        self.recv = torch.zeros(blk * world, dtype=torch.float32)
+        self.minmax = torch.zeros(2, dtype=torch.float32)
+        self.ldisp = np.zeros((2 * self.hl, n, 4), np.float32)
+        self.lnorm = np.zeros((2 * self.hl, n, 4), np.float32)
+        self.amp = np.zeros(1, np.float32)
+        self.t = 0.0
+        self.fused = False
+
+    def _phase(self, phase):
+        p = lambda x: x.ctypes.data_as(C.c_void_p)
+        tp = lambda x: C.c_void_p(x.data_ptr())
+        rc = lib().wso_emu_slab_rank_phase(self.logn, self.variant, self.shift, self.rank, phase, p(self.amp_t),
+                                           p(self.om_t), p(self.kv), self.omega0, self.lam, self.t, tp(self.send),
+                                           tp(self.recv), tp(self.minmax), p(self.ldisp), p(self.lnorm), p(self.amp))
+        if rc != 0:
+            raise ValueError(f"emulated slab phase failed rc={rc}")
+
+    def pass1(self, t):
+        self.t = float(t)
+        self.minmax[0], self.minmax[1] = 3.402823466e+38, 1.17549435e-38
+        self._phase(0)
+
+    def heights(self): self._phase(1)
+    def pass2(self): self._phase(2)
+    def sync(self): pass
+    def read_heights(self): return self.amp[0], np.float32(self.minmax[0]), np.float32(self.minmax[1])
+    def local_rows(self, which): return self.ldisp if which == 0 else self.lnorm
+
+    def row_index(self):
+        rows = np.zeros(2 * self.hl, np.uint32)
+        for ml in range(self.hl):
+            mp = self.rank * self.hl + ml
+            rows[ml] = mp
+            rows[self.hl + ml] = self.n // 2 if mp == 0 else self.n - mp
+        return rows

@@ -1,0 +1,67 @@
+"""torchrun worker of tests/test_slab.py::test_slab_two_gpus_vs_oracle (and of tools runs): every rank computes its
+slab of one N x N tile-frame; rank 0 checks the gathered maps against the oracle."""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=2048)
+    ap.add_argument("--fused", type=int, default=0)
+    ap.add_argument("--pair", type=int, default=0)
+    ap.add_argument("--out", default="")
+    a = ap.parse_args()
+    rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(lr)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    from conftest import SCALAR_REL_TOL, assert_maps_close
+    from oracle import port as P
+    from watersurfacerendering_b200.slab import SlabBackend, SlabOcean
+    n = a.n
+    p = P.OceanParams(tile_size=n, tile_length=1000.0 * n / 512)
+    o = P.PortOracle(p)
+    rng = np.random.default_rng(n)
+    xi = (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))).astype(np.complex64)
+    o.prepare(xi)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    b = SlabBackend(n, p.tile_length, rank, world, lr)
+    b.set_stream(stream.cuda_stream)
+    b.force_pair(bool(a.pair))
+    b.import_h0(o.h0)
+    ocean = SlabOcean(b, fused=bool(a.fused))
+    msg = "ok"
+    for t in (0.0, 12.5):
+        ocean.compute(t)
+        b.sync()
+        torch.cuda.synchronize()
+        disp, norm = ocean.gather_maps()
+        amp, mn, mx = b.read_heights()
+        if rank == 0:
+            a_ref, d_ref, n_ref = o.compute_waves(t)
+            try:
+                assert_maps_close(disp, norm, d_ref, n_ref, f"slab x{world} fused={a.fused} t={t}")
+                assert abs(amp - a_ref) <= SCALAR_REL_TOL * a_ref, (amp, a_ref)
+            except AssertionError as ex:
+                msg = "FAIL " + str(ex)
+    if rank == 0 and a.out:
+        open(a.out, "w").write(msg)
+    if rank == 0:
+        print("slab_worker:", msg)
+    dist.barrier()
+    b.close()
+    dist.destroy_process_group()
+    sys.exit(0 if msg == "ok" else 1)
+
+
+if __name__ == "__main__":
+    main()

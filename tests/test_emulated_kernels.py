@@ -83,3 +83,24 @@ def test_one_hot_layout():
             assert np.abs(disp[..., :3] - d_ref[..., :3]).max() <= 2e-6 * scale, (m, c)
             scale = max(np.abs(n_ref).max(), 1e-30)
             assert np.abs(norm - n_ref).max() <= 2e-6 * scale, (m, c)
+
+
+@pytest.mark.parametrize("name,variant,world", [("n64_default", 0, 1), ("n64_default", 0, 2), ("n64_wind", 0, 4),
+                                                 ("n64_wind", 1, 2), ("n64_default", 1, 8), ("n256_default", 0, 4),
+                                                 ("n256_default", 1, 2)])
+def test_emulated_slab_decomposition_matches_single_device(name, variant, world):
+    """Slab path (BASELINE config 5) on `world` emulated devices: K1 stores = the transpose into the row owners'
+    buffers, min/max reduced over ranks, K2 on local rows (variant 1: the two-CTA cluster-pair K2).  Must agree
+    with the single-device kernels BIT FOR BIT (same arithmetic, different placement) and with the fixture."""
+    g, params = load_golden(name)
+    h0 = g["h0"]
+    n = params["tile_size"]
+    i = len(g["t"]) - 1
+    t = float(g["t"][i])
+    a1, d1, n1, mn1, mx1, _ = E.compute(n, params["tile_length"], params["lam"], h0[..., 0], h0[..., 1], h0[..., 4], t,
+                                        anim_period=params["anim_period"])
+    a, disp, norm, mn, mx = E.compute_slab(n, params["tile_length"], params["lam"], h0[..., 0], h0[..., 1], h0[..., 4],
+                                           t, world, variant=variant, anim_period=params["anim_period"])
+    assert (a, mn, mx) == (a1, mn1, mx1)
+    assert disp.tobytes() == d1.tobytes() and norm.tobytes() == n1.tobytes()
+    assert_maps_close(disp, norm, g["disp"][i], g["norm"][i], f"{name} slab x{world}")

@@ -1,0 +1,185 @@
+"""Slab-decomposed path (BASELINE configs[4]).
+
+CPU (-m "not gpu"): the real SlabOcean orchestration (all-to-all transpose + min/max all-reduce) over world_size-2
+gloo, with the emulated kernel bodies (tests/emu) as the per-rank backend, against the reference fixture.
+GPU (-m gpu): the CUDA slab kernels through the C ABI - world 1 in-process (incl. the two-CTA cluster K2), and
+2 ranks under torchrun when the box has >= 2 GPUs - against the oracle at N = 2048 and the fixtures at N = 64/256.
+"""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT, SCALAR_REL_TOL, assert_maps_close, h0_struct, load_golden
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _emu_worker(rank, world, port, name, variant, q):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from emu import driver as E
+    from watersurfacerendering_b200.slab import SlabOcean
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g, params = load_golden(name)
+    h0 = g["h0"]
+    i = len(g["t"]) - 1
+    b = E.EmuSlabBackend(params["tile_size"], params["tile_length"], params["lam"], h0[..., 0], h0[..., 1], h0[..., 4],
+                         rank, world, variant=variant, anim_period=params["anim_period"])
+    ocean = SlabOcean(b, fused=False)
+    ocean.compute(float(g["t"][i]))
+    disp, norm = ocean.gather_maps()
+    a, mn, mx = b.read_heights()
+    ok = True
+    try:
+        assert_maps_close(disp, norm, g["disp"][i], g["norm"][i], f"{name} rank {rank}")
+        assert abs(a - g["A"][i]) <= SCALAR_REL_TOL * g["A"][i]
+        assert abs(mn - g["minh"][i]) <= SCALAR_REL_TOL * g["A"][i]
+        assert abs(mx - g["maxh"][i]) <= SCALAR_REL_TOL * g["A"][i]
+        msg = ""
+    except AssertionError as ex:  # report through the queue: a spawned process cannot fail the test by itself
+        ok, msg = False, str(ex)
+    q.put((rank, ok, msg, float(a)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name,variant", [("n64_default", 0), ("n64_wind", 1)])
+def test_two_rank_gloo_slab_exchange(name, variant):
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_emu_worker, args=(r, world, port, name, variant, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok, msg, a in res:
+        assert ok, f"rank {rank}: {msg}"
+    assert res[0][3] == res[1][3]   # both ranks agree on the global amplitude
+
+
+def test_counter_gauss_is_deterministic_and_normal():
+    """The counter-based Gaussian source behind wso_slab_prepare_counter: same (seed, index) -> same draw on every rank,
+    moments of a standard normal, and h0 conjugate symmetry as the kernels require."""
+    import watersurfacerendering_b200 as W
+    from watersurfacerendering_b200 import _lib as L
+    from watersurfacerendering_b200.slab import counter_h0
+    import ctypes as C
+    p = L.WsoParams()
+    L.load().wso_default_params(C.byref(p))
+    p.tile_size, p.tile_length = 256, 500.0
+    a = counter_h0(p, 7, 0, 256)
+    b = counter_h0(p, 7, 64, 32)
+    assert a[64:96].tobytes() == b.tobytes()
+    c = counter_h0(p, 8, 64, 32)
+    assert c.tobytes() != b.tobytes()
+    assert np.array_equal(a["re"], a["re_c"]) and np.array_equal(a["im"], -a["im_c"])
+    assert a["omega"][128, 128] == 0 and a["re"][128, 128] == 0   # DC bin (reference: k = 0 at index N/2)
+    # xi recovered from a flat spectrum: unit variance, zero mean, uncorrelated parts
+    p.phillips_const = 1.0
+    amp = counter_h0(p, 7, 0, 256)
+    z = amp["re"] + 1j * amp["im"]
+    mask = np.abs(z) > 0
+    ph = np.angle(z[mask])
+    assert abs(np.mean(np.cos(ph))) < 0.02 and abs(np.mean(np.sin(ph))) < 0.02
+
+
+# --------------------------------------------------------------------------------------------------- GPU
+def _oracle(n, seed=0):
+    from oracle import port as P
+    p = P.OceanParams(tile_size=n, tile_length=1000.0 * n / 512)
+    o = P.PortOracle(p)
+    rng = np.random.default_rng(seed + n)
+    xi = (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))).astype(np.complex64)
+    o.prepare(xi)
+    return p, o
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,pair", [("n64_default", False), ("n64_wind", True), ("n256_default", False),
+                                       ("n256_default", True)])
+def test_slab_world1_fixtures(name, pair):
+    from watersurfacerendering_b200.slab import SlabBackend, SlabOcean
+    g, params = load_golden(name)
+    b = SlabBackend(params["tile_size"], params["tile_length"], 0, 1, 0, lambda_=params["lam"],
+                    anim_period=params["anim_period"], wind_dir_x=params["wind_x"], wind_dir_y=params["wind_y"],
+                    wind_speed=params["wind_speed"], phillips_const=params["phillips_const"], damping=params["damping"])
+    try:
+        b.force_pair(pair)
+        b.import_h0(h0_struct(g["h0"]))
+        ocean = SlabOcean(b)
+        for i, t in enumerate(g["t"]):
+            ocean.compute(float(t))
+            b.sync()
+            disp, norm = ocean.gather_maps()
+            assert_maps_close(disp, norm, g["disp"][i], g["norm"][i], f"{name} pair={pair} t={t}")
+            a, mn, mx = b.read_heights()
+            assert abs(a - g["A"][i]) <= SCALAR_REL_TOL * g["A"][i]
+            assert abs(mn - g["minh"][i]) <= SCALAR_REL_TOL * g["A"][i]
+            assert abs(mx - g["maxh"][i]) <= SCALAR_REL_TOL * g["A"][i]
+    finally:
+        b.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pair", [False, True])
+def test_slab_world1_2048_vs_oracle_and_batched_path(pair):
+    """N = 2048 through the slab kernels on one device: vs the oracle (tolerance gate) and vs the regular batched
+    path (bit-exact: same arithmetic, different data placement)."""
+    import watersurfacerendering_b200 as W
+    from watersurfacerendering_b200.slab import SlabBackend, SlabOcean
+    n = 2048
+    p, o = _oracle(n)
+    t = 12.5
+    a_ref, d_ref, n_ref = o.compute_waves(t)
+    b = SlabBackend(n, p.tile_length, 0, 1, 0)
+    try:
+        b.force_pair(pair)
+        b.import_h0(o.h0)
+        ocean = SlabOcean(b)
+        ocean.compute(t)
+        b.sync()
+        disp, norm = ocean.gather_maps()
+        a, mn, mx = b.read_heights()
+    finally:
+        b.close()
+    assert_maps_close(disp, norm, d_ref, n_ref, f"slab 2048 pair={pair}")
+    assert abs(a - a_ref) <= SCALAR_REL_TOL * a_ref
+    with W.WSTessendorf(n, p.tile_length) as ws:
+        ws.ImportH0(o.h0)
+        a2 = ws.ComputeWaves(t)
+        assert a2 == a
+        assert ws.GetDisplacements().tobytes() == disp.tobytes()
+        assert ws.GetNormals().tobytes() == norm.tobytes()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fused", [0, 1])
+def test_slab_two_gpus_vs_oracle(fused, tmp_path):
+    """2 ranks under torchrun: all-to-all (NCCL) and fused peer-store exchange, N = 2048 vs the oracle."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    out = tmp_path / "res.txt"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "slab_worker.py"), "--n", "2048",
+           "--fused", str(fused), "--out", str(out)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert out.read_text().strip() == "ok", out.read_text()

@@ -72,6 +72,28 @@ SYMBOLS = {
     "wso_get_stats": (_int, [_vp, C.POINTER(C.c_uint64), C.POINTER(_u32)]),
     "wso_set_profiling": (_int, [_vp, _int]),
     "wso_get_profile": (_int, [_vp, _vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    # slab-decomposed path (one large grid over several devices)
+    "wso_slab_create": (_int, [_pp, _int, _u32, _u32, C.POINTER(_vp)]),
+    "wso_slab_destroy": (_int, [_vp]),
+    "wso_slab_import_h0": (_int, [_vp, _vp]),
+    "wso_slab_prepare_counter": (_int, [_vp, C.c_uint64]),
+    "wso_counter_h0": (_int, [_pp, C.c_uint64, _u32, _u32, _vp]),
+    "wso_slab_set_lambda": (_int, [_vp, _f32]),
+    "wso_slab_set_stream": (_int, [_vp, _vp]),
+    "wso_slab_buffers": (_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_size_t), C.POINTER(_vp)]),
+    "wso_slab_ipc_handle": (_int, [_vp, _vp]),
+    "wso_slab_open_peer": (_int, [_vp, _u32, _vp]),
+    "wso_slab_set_fused": (_int, [_vp, _int]),
+    "wso_slab_force_pair": (_int, [_vp, _int]),
+    "wso_slab_pass1": (_int, [_vp, _f32]),
+    "wso_slab_heights": (_int, [_vp]),
+    "wso_slab_pass2": (_int, [_vp]),
+    "wso_slab_sync": (_int, [_vp]),
+    "wso_slab_read_heights": (_int, [_vp, C.POINTER(_f32), C.POINTER(_f32), C.POINTER(_f32)]),
+    "wso_slab_map_device": (_int, [_vp, _int, C.POINTER(_vp), C.POINTER(_u32)]),
+    "wso_slab_copy_rows": (_int, [_vp, _int, _vp]),
+    "wso_slab_row_index": (_int, [_vp, _vp]),
+    "wso_slab_last_error": (C.c_char_p, [_vp]),
     "wso_last_error": (C.c_char_p, [_vp]),
     "wso_version": (C.c_char_p, []),
 }
@@ -105,4 +127,10 @@ class WsoError(RuntimeError):
 def check(status: int, ctx=None):
     if status != WSO_OK:
         msg = load().wso_last_error(ctx)
+        raise WsoError(status, msg.decode() if msg else "")
+
+
+def check_slab(status: int, slab=None):
+    if status != WSO_OK:
+        msg = load().wso_slab_last_error(slab)
         raise WsoError(status, msg.decode() if msg else "")

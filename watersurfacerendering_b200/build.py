@@ -17,7 +17,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 INCLUDE = os.path.join(ROOT, "include")
 LIB_PATH = os.path.join(PKG_DIR, "libwsocean.so")
 
-SOURCES = ["wso_kernels.cu", "wso_api.cu", "wso_host_prepare.cpp"]
+SOURCES = ["wso_kernels.cu", "wso_slab_kernels.cu", "wso_api.cu", "wso_slab.cu", "wso_host_prepare.cpp"]
 HEADERS = ["wso_device.cuh", "wso_kernels.cuh", "wso_launch.h", "wso_host_prepare.h"]
 
 NVCC_FLAGS = [
@@ -25,7 +25,7 @@ NVCC_FLAGS = [
     "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden,-ffp-contract=off,-O2",
     "-Xptxas", "-v",
-    "--shared", "-cudart", "static",
+    "--shared", "-cudart", "static", "--threads", "0",
 ]
 
 

@@ -227,7 +227,7 @@ int upload_h0(wso_ctx* c, uint32_t tile, const wso_h0_record* h0) {
                 const int j = (int)std::nearbyint(r.dispersion / omega0);
                 std::memcpy(&wfield, &j, sizeof(float));
             }
-            rec[(size_t)k * n + m] = make_float4(r.amp_re, r.amp_im, inv, wfield);
+            rec[wso::h0_index((int)k, (int)m, (int)n, 0)] = make_float4(r.amp_re, r.amp_im, inv, wfield);
         }
     // pair-summed records for the interior (i,j >= 1): amplitude h0(k) + h0(-k); 1/|k| and omega are even in k
     const uint32_t hN = n / 2;
@@ -235,8 +235,9 @@ int upload_h0(wso_ctx* c, uint32_t tile, const wso_h0_record* h0) {
     bool pairs_ok = true;  // needs omega(k) == omega(-k): true for any dispersion that depends on |k| only
     for (uint32_t j = 1; j < hN; ++j)
         for (uint32_t i = 1; i < hN; ++i) {
-            const float4 a0 = rec[(size_t)j * n + i], a3 = rec[(size_t)(n - j) * n + (n - i)];
-            const float4 a1 = rec[(size_t)(n - j) * n + i], a2 = rec[(size_t)j * n + (n - i)];
+            const int N_ = (int)n;
+            const float4 a0 = rec[wso::h0_index((int)j, (int)i, N_, 0)], a3 = rec[wso::h0_index(N_ - (int)j, N_ - (int)i, N_, 0)];
+            const float4 a1 = rec[wso::h0_index(N_ - (int)j, (int)i, N_, 0)], a2 = rec[wso::h0_index((int)j, N_ - (int)i, N_, 0)];
             if (std::memcmp(&a0.w, &a3.w, 4) != 0 || std::memcmp(&a1.w, &a2.w, 4) != 0) pairs_ok = false;
             recs[((size_t)j * hN + i) * 2 + 0] = make_float4(a0.x + a3.x, a0.y + a3.y, a0.z, a0.w);
             recs[((size_t)j * hN + i) * 2 + 1] = make_float4(a1.x + a2.x, a1.y + a2.y, a1.z, a1.w);

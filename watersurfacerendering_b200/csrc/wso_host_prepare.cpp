@@ -86,48 +86,78 @@ void host_gauss_array_from_rand(uint32_t n, std::vector<float>& xi) {
     }
 }
 
+H0Builder::H0Builder(const wso_params& p) {
+    const DerivedParams d = derive_params(p);
+    wind_x = d.wind_x;
+    wind_y = d.wind_y;
+    base_freq = d.base_freq;
+    phillips_const = p.phillips_const;
+    damping = p.damping;
+    inv_sqrt2 = 1.0f / std::sqrt(2.0f);   // reference: WSTessendorf.h:231
+    const float Lw = d.wind_speed * d.wind_speed / kGravity;
+    Lw2 = Lw * Lw;
+}
+
+wso_h0_record H0Builder::at(float kx, float kz, float xi_re, float xi_im) const {
+    const float dot = kx * kx + kz * kz;
+    const float k = std::sqrt(dot);
+    wso_h0_record r;
+    if (k > 0.00001f) {
+        const float inv = 1.0f / std::sqrt(dot);
+        const float ux = kx * inv, uz = kz * inv;
+        // Phillips spectrum (reference: WSTessendorf.h:249-263); (k^.w)^2 is even in k^, so the
+        // "conjugate" amplitude built from -k^ equals conj(amplitude) exactly.
+        const float k2 = k * k;
+        const float k4 = k2 * k2;
+        float cf = ux * wind_x + uz * wind_y;
+        cf = cf * cf;
+        const float ph = phillips_const * std::exp(-1.0f / (k2 * Lw2)) / k4 * cf * std::exp(-k2 * damping * damping);
+        const float s = std::sqrt(ph);
+        r.amp_re = inv_sqrt2 * xi_re * s;       // reference: WSTessendorf.h:237-243
+        r.amp_im = inv_sqrt2 * xi_im * s;
+        r.amp_conj_re = r.amp_re;
+        r.amp_conj_im = -r.amp_im;
+        // reference: QDispersion, WSTessendorf.h:284-297
+        r.dispersion = std::floor(std::sqrt(kGravity * k) / base_freq) * base_freq;
+    } else {
+        r.amp_re = r.amp_im = r.amp_conj_re = 0.0f;
+        r.amp_conj_im = -0.0f;
+        r.dispersion = 0.0f;
+    }
+    return r;
+}
+
 void host_base_wave_heights(const wso_params& p, const float* xi, std::vector<wso_h0_record>& h0) {
     const uint32_t n = p.tile_size;
-    const DerivedParams d = derive_params(p);
+    const H0Builder hb(p);
     h0.resize((size_t)n * n);
     std::vector<float> kv;
     host_wave_numbers(n, p.tile_length, kv);
-    const float inv_sqrt2 = 1.0f / std::sqrt(2.0f);   // reference: WSTessendorf.h:231
-    const float Lw = d.wind_speed * d.wind_speed / kGravity;
-    const float Lw2 = Lw * Lw;
-    for (uint32_t m = 0; m < n; ++m) {
+    for (uint32_t m = 0; m < n; ++m)
         for (uint32_t c = 0; c < n; ++c) {
             const size_t i = (size_t)m * n + c;
-            const float kx = kv[c], kz = kv[m];
-            const float dot = kx * kx + kz * kz;
-            const float k = std::sqrt(dot);
-            wso_h0_record r;
-            if (k > 0.00001f) {
-                const float inv = 1.0f / std::sqrt(dot);
-                const float ux = kx * inv, uz = kz * inv;
-                // Phillips spectrum (reference: WSTessendorf.h:249-263); (k^.w)^2 is even in k^, so the
-                // "conjugate" amplitude built from -k^ equals conj(amplitude) exactly.
-                const float k2 = k * k;
-                const float k4 = k2 * k2;
-                float cf = ux * d.wind_x + uz * d.wind_y;
-                cf = cf * cf;
-                const float ph = p.phillips_const * std::exp(-1.0f / (k2 * Lw2)) / k4 * cf *
-                                 std::exp(-k2 * p.damping * p.damping);
-                const float s = std::sqrt(ph);
-                r.amp_re = inv_sqrt2 * xi[2 * i] * s;       // reference: WSTessendorf.h:237-243
-                r.amp_im = inv_sqrt2 * xi[2 * i + 1] * s;
-                r.amp_conj_re = r.amp_re;
-                r.amp_conj_im = -r.amp_im;
-                // reference: QDispersion, WSTessendorf.h:284-297
-                r.dispersion = std::floor(std::sqrt(kGravity * k) / d.base_freq) * d.base_freq;
-            } else {
-                r.amp_re = r.amp_im = r.amp_conj_re = 0.0f;
-                r.amp_conj_im = -0.0f;
-                r.dispersion = 0.0f;
-            }
-            h0[i] = r;
+            h0[i] = hb.at(kv[c], kv[m], xi[2 * i], xi[2 * i + 1]);
         }
-    }
+}
+
+// Counter-based Gaussian pair for wave vector index idx = m*N + n: a 64-bit mix of (seed, idx) -> two uniforms ->
+// Box-Muller.  Used where the reference's serial rand() stream is impractical (a 16384^2 grid generated in slabs on
+// several devices); the same function serves the product and, through wso_counter_gauss(), its checkers.
+static inline uint64_t mix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+void counter_gauss(uint64_t seed, uint64_t idx, float* re, float* im) {
+    const uint64_t u = mix64(mix64(seed) ^ mix64(idx + 0x632BE59BD9B4E019ull));
+    const double u1 = ((double)(u >> 40) + 1.0) * (1.0 / 16777216.0);        // (0, 1]
+    const double u2 = (double)((u >> 8) & 0xFFFFFFull) * (1.0 / 16777216.0);  // [0, 1)
+    const double r = std::sqrt(-2.0 * std::log(u1));
+    const double a = 2.0 * M_PI * u2;
+    *re = (float)(r * std::cos(a));
+    *im = (float)(r * std::sin(a));
 }
 
 }  // namespace wso

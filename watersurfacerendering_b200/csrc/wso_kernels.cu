@@ -160,7 +160,7 @@ static cudaError_t launch_all(const LaunchArgs& args, int n_items, cudaStream_t 
     // small parameter block
     constexpr int bulk_ctas_per_item = ((1 << LOGN) / 2 / B::CP) * (4 / B::NF);
     if (n_items <= kSmallChunk && n_items * bulk_ctas_per_item < 2 * 148) {
-        LaunchArgsSmall sm;
+        LaunchArgsSmall sm = {};
         sm.tw = args.tw; sm.W = args.W; sm.disp = args.disp; sm.norm = args.norm;
         sm.minmax = args.minmax; sm.amp_out = args.amp_out;
         for (int i = 0; i < kSmallChunk; ++i) { sm.items[i] = args.items[i]; sm.td[i] = args.td[i]; }

@@ -21,12 +21,13 @@ static constexpr int kMaxTable = 1024;  // entries of the per-frame sincos table
 
 // Per-tile constants, device pointers (written once per Prepare()).
 struct TileDev {
-    // [n][m] (TRANSPOSED) one 16-byte record per wave vector (m,n):
+    // [jl][half][m] one 16-byte record per wave vector (m,n), grouped by column PAIR: local pair jl = j - j0,
+    // half 0 = column n = j, half 1 = its mirror column n = N-j (n = N/2 for j = 0); m runs contiguously:
     //   x,y = heightAmp re,im (reference h0 record)          z = 1/|k| (0 where |k| <= 1e-5: WSTessendorf.h:135)
     //   w   = quantised dispersion omega (WSTessendorf.h:284-287), or - when table_len > 0 - its integer
     //         multiple j of the base frequency (omega == fl(float(j)*omega0) exactly, checked at Prepare)
     const float4* h0;
-    // [j][i][2] for column pair j = (j, N-j) and row pair i = (i, N-i), i,j in [0, N/2): the same record with
+    // [jl][i][2] for column pair j = j0 + jl = (j, N-j) and row pair i = (i, N-i), i in [0, N/2): the same record with
     // the amplitude replaced by the sum over the mirror pair, h0(k) + h0(-k):
     //   [0]: k = (m=i, n=j)     [1]: k = (m=i, n=N-j)
     // Only Re FFT is kept, so away from the index-0 / N/2 lines every field depends on h~ only through
@@ -37,7 +38,16 @@ struct TileDev {
     float omega0;        // base frequency (float)(2*pi/T)
     int table_len;       // j_max+1 when the per-frame sincos table is usable, else 0
     int use_pairs;       // 1 when omega(k) == omega(-k) everywhere (always true for Prepare()-built h0): hs is valid
+    int j0;              // first column pair held by this device (0 unless the grid is slab-decomposed)
 };
+
+// Position of wave vector (m, n) in TileDev::h0 for a device whose first column pair is j0.
+WSO_HD size_t h0_index(int n, int m, int N, int j0) {
+    const int H = N >> 1;
+    const int j = (n < H) ? n : ((n == H) ? 0 : N - n);
+    const int half = (n < H) ? 0 : 1;
+    return ((size_t)(j - j0) * 2 + half) * N + m;
+}
 
 struct BatchItem {
     uint32_t tile;  // which h0 / parameter set (host bookkeeping; the kernels read td[] below)
@@ -56,6 +66,13 @@ struct LaunchArgsT {
     float4* norm;          // [slot][N*N]
     float* minmax;         // [slot][2]
     float* amp_out;        // [slot] amplitude A
+    // Slab decomposition of ONE grid over P = 2^slab_shift devices: this device runs K1 on the column
+    // pairs [rank*Hl, (rank+1)*Hl), Hl = N/2/P, and K2h/K2 on the row items m' of the same range.  K1 writes the block
+    // [ml][f][half][jl] destined for the owner d of row item m' = d*Hl + ml through Wdst[d] (the owner's receive
+    // buffer over NVLink peer memory, or the local send buffer of an all-to-all); K2h/K2 read W = [src][ml][f][half][jl].
+    int slab_shift;
+    int slab_rank;
+    float2* Wdst[8];
     BatchItem items[CAP];
     // the tile constants of every item travel by value in the kernel parameters (constant bank): no dependent
     // global load sits between CTA start and the first h0 request
@@ -159,7 +176,7 @@ WSO_HD void pack_interior(float s0, float kx0, float kz0, float inv0, float s1, 
 // -------------------------------------------------------------------------------------------------
 // K1
 // -------------------------------------------------------------------------------------------------
-template <int LOGN, int CP, int NF>
+template <int LOGN, int CP, int NF, bool SLAB = false>
 struct Pass1 {
     static constexpr int N = 1 << LOGN;
     static constexpr int H = N / 2;
@@ -205,15 +222,19 @@ struct Pass1 {
 
     // one work item on the index-0 / N/2 lines (or any item when the pair records are unusable):
     // rows (mA,mB) x columns (nA,nB) = 4 wave vectors from the per-point records, general mirror pattern
+    // jl: column pair index local to this device (storage), j = td.j0 + jl: global (wave numbers, special cases)
     template <bool TABLE>
     static WSO_HD void evolve_item_general(const TileDev& td, const float2* table, float t, int fg, float2* smem,
-                                           int cp, int i, int j) {
+                                           int cp, int i, int jl) {
+        const int j = td.j0 + jl;
         const int mA = i, mB = (i == 0) ? H : N - i;
         const int nA = j, nB = (j == 0) ? H : N - j;
         const float kxA = td.kv[nA], kxB = td.kv[nB], kzA = td.kv[mA], kzB = td.kv[mB];
         const int eA = pad_idx(mA), eB = pad_idx(mB);
-        const float4 q0 = td.h0[nA * N + mA], q1 = td.h0[nB * N + mA];
-        const float4 q2 = td.h0[nA * N + mB], q3 = td.h0[nB * N + mB];
+        const float4* colA = td.h0 + (size_t)jl * 2 * N;
+        const float4* colB = colA + N;
+        const float4 q0 = colA[mA], q1 = colB[mA];
+        const float4 q2 = colA[mB], q3 = colB[mB];
         const float h0 = eval_height<TABLE>(q0, table, t), h1 = eval_height<TABLE>(q1, table, t);
         const float h2 = eval_height<TABLE>(q2, table, t), h3 = eval_height<TABLE>(q3, table, t);
         const int mask = ((i != 0) ? 2 : 0) | ((j != 0) ? 1 : 0);
@@ -267,8 +288,8 @@ struct Pass1 {
             float4 q0[CPT], q1[CPT];
 #pragma unroll
             for (int k = 0; k < CPT; ++k) {
-                const int j = bx * CP + cg + k * CG;
-                const float4* rec = td.hs + ((size_t)j * H + i) * 2;
+                const int jl = bx * CP + cg + k * CG;
+                const float4* rec = td.hs + ((size_t)jl * H + i) * 2;
                 q0[k] = rec[0];
                 q1[k] = rec[1];
             }
@@ -277,13 +298,13 @@ struct Pass1 {
 #pragma unroll
             for (int k = 0; k < CPT; ++k) {
                 const int cp = cg + k * CG;
-                const int j = bx * CP + cp;
+                const int j = td.j0 + bx * CP + cp;
                 if (j != 0) {
                     const float s0 = 0.5f * eval_height<TABLE>(q0[k], table, t);
                     const float s1 = 0.5f * eval_height<TABLE>(q1[k], table, t);
                     pack_interior_item(smem, fg, cp, eA, eB, s0, s1, td.kv[j], td.kv[N - j], kzA, q0[k].z, q1[k].z);
                 } else {
-                    evolve_item_general<TABLE>(td, table, t, fg, smem, cp, i, j);
+                    evolve_item_general<TABLE>(td, table, t, fg, smem, cp, i, bx * CP + cp);
                 }
             }
         }
@@ -347,7 +368,7 @@ struct Pass1 {
         float2* Wit = args.W + (size_t)bz * ((size_t)H * 4 * N);
         ex.each([&](int tid, ThreadState&) {
             const int cp = tid % CP;
-            const int j = bx * CP + cp;
+            const int jl = bx * CP + cp;
             for (int rest = tid / CP; rest < NF * H; rest += T / CP) {
                 const int mp = rest % H;
                 const int fl = rest / H;
@@ -361,9 +382,19 @@ struct Pass1 {
                     wa.y = ch.x;
                     wb.y = ch.y;
                 }
-                float2* dst = Wit + ((size_t)mp * 4 + (by * NF + fl)) * N + j;
-                dst[0] = wa;
-                dst[H] = wb;
+                const int f = by * NF + fl;
+                if constexpr (SLAB) {
+                    // the store IS the transpose: block of the device that owns row item m'
+                    const int hl_log = LOGN - 1 - args.slab_shift;
+                    const int Hl = 1 << hl_log;
+                    float2* dst = args.Wdst[mp >> hl_log] + ((size_t)((mp & (Hl - 1)) * 4 + f) * 2) * Hl + jl;
+                    dst[0] = wa;
+                    dst[Hl] = wb;
+                } else {
+                    float2* dst = Wit + ((size_t)mp * 4 + f) * N + jl;
+                    dst[0] = wa;
+                    dst[H] = wb;
+                }
             }
         });
     }
@@ -388,24 +419,35 @@ WSO_HD float amplitude_of(float mn, float mx) {
 //                      (A = max(|min|,|max|) must be known before any disp.y can be written normalised).
 // HEIGHT_ONLY = false: K2  - all four fields; by = 0 writes the displacement map (fields 0,1; disp.y already
 //                      multiplied by 1/A), by = 1 the normal map (fields 2,3).
-template <int LOGN, int RI, bool HEIGHT_ONLY>
+// SLAB : the grid is slab-decomposed over several devices (LaunchArgsT::slab_*): W is read in the received block
+//        layout and the two output rows of local row item ml go to local rows ml and Hl + ml.
+// PAIR : the two lines of a row item live in the two CTAs of a thread-block cluster (a 16384-point line pair does not
+//        fit one SM's shared memory): each CTA transforms one line, then packs ONE of the two output rows, reading
+//        its partner's line through distributed shared memory.
+template <int LOGN, int RI, bool HEIGHT_ONLY, bool SLAB = false, bool PAIR = false>
 struct Pass2 {
     static constexpr int N = 1 << LOGN;
     static constexpr int H = N / 2;
     static constexpr int LPI = HEIGHT_ONLY ? 1 : 2;  // lines per row item
-    static constexpr int B = RI * LPI;
+    static constexpr int LPC = PAIR ? 1 : LPI;       // ... of which this CTA holds
+    static constexpr int B = RI * LPC;
     static constexpr int T = B * N / kValsPerThread;
     static constexpr int G = N / kValsPerThread;     // threads per line
-    static constexpr int GI = LPI * G;               // threads per row item
+    static constexpr int GI = LPC * G;               // threads per row item
     static constexpr int LS = LineStride<N>::value;
     static constexpr int SMEM_BYTES = B * LS * (int)sizeof(float2);
     static_assert(T >= 1 && T <= 1024, "bad CTA size");
     static_assert(H % RI == 0, "bad tiling");
+    static_assert(!PAIR || (!HEIGHT_ONLY && RI == 1), "cluster pairs: one row item per CTA pair");
 
+    template <class Args>
+    static WSO_HD int hl_log(const Args& args) { return SLAB ? LOGN - 1 - args.slab_shift : LOGN - 1; }
+
+    // ---- transform phase: first stage straight from global memory (W rows are contiguous), rest in shared memory
+    // crank: rank of this CTA in its cluster pair (PAIR only)
     template <class Exec, class Args>
-    static WSO_HD void run(Exec& ex, float2* smem, int bx, int by, int bz, const Args& args) {
-        const BatchItem item = args.items[bz];
-        const float2* Wit = args.W + (size_t)bz * ((size_t)H * 4 * N);
+    static WSO_HD void transform(Exec& ex, float2* smem, int bx, int by, int bz, int crank, const Args& args) {
+        const float2* Wit = args.W + (SLAB ? (size_t)0 : (size_t)bz * ((size_t)H * 4 * N));
         // K2h consumes what K1 (its predecessor in the stream) wrote: wait first.  K2 is released by K2h only after
         // K2h's own wait, i.e. K1 is complete when K2 starts: K2 transforms W right away and waits (for K2h's
         // min/max) only before the pack phase.
@@ -413,119 +455,162 @@ struct Pass2 {
             ex.pdl_wait();
             ex.pdl_release();
         }
-
-        // ---- first stage straight from global memory (W rows are contiguous) ---------------------
-        {
-            constexpr int R = Plan<LOGN>::R[0];
-            using St = Stage<N, B, R, 1>;
-            ex.each([&](int tid, ThreadState& st) {
-                const int line = tid / G;
-                const int mp = bx * RI + line / LPI;
-                const int f = HEIGHT_ONLY ? 0 : by * 2 + (line % LPI);
-                const float2* src = Wit + ((size_t)mp * 4 + f) * N;
+        constexpr int R = Plan<LOGN>::R[0];
+        using St = Stage<N, B, R, 1>;
+        const int hlog = hl_log(args);
+        ex.each([&](int tid, ThreadState& st) {
+            const int line = tid / G;
+            const int ml = bx * RI + line / LPC;
+            const int f = HEIGHT_ONLY ? 0 : by * 2 + (PAIR ? crank : line % LPC);
+            const float2* src = Wit + ((size_t)ml * 4 + f) * 2 * ((size_t)1 << hlog);  // [ml][f][half][jl] of source 0
 #pragma unroll
-                for (int i = 0; i < St::NB; ++i) {
-                    const int j = tid % G + G * i;
+            for (int i = 0; i < St::NB; ++i) {
+                const int j = tid % G + G * i;
 #pragma unroll
-                    for (int r = 0; r < R; ++r) st.v[i * R + r] = src[slot_of_column(j + r * St::JN, N)];
-                }
-                St::twiddle_dft(args.tw, tid, st);
-                St::store(smem, tid, st);
-            });
-            ex.template sync_group<G, T>(1);
-            if constexpr (Plan<LOGN>::S > 1) RunStages<LOGN, B, 1, R, Exec>::run(ex, smem, args.tw);
-        }
-        // the pack phase of a row item reads both of its lines: barrier over that pair of line groups
-        if constexpr (LPI == 2) ex.template sync_group<GI, T>(1 + (G > 32 ? B : 0));
-
-        if constexpr (HEIGHT_ONLY) {
-            ex.each([&](int tid, ThreadState& st) {
-                float mn = kInitMin, mx = kInitMax;
-                const int ri = tid / GI, lt = tid % GI;
-                const int mp = bx * RI + ri;
-                const float2* l0 = smem + ri * LS;
-                // (-1)^(row+col): loop invariant when the column stride GI is even (N >= 32)
-                float s = ((mp + lt) & 1) ? -1.0f : 1.0f;
-                if (mp != 0) {
-                    for (int c = lt; c < N; c += GI) {
-                        if (GI & 1) s = ((mp + c) & 1) ? -1.0f : 1.0f;
-                        const float h = rmul(l0[pad_idx(c)].x, s);
-                        mn = h < mn ? h : mn;
-                        mx = h > mx ? h : mx;
-                    }
-                } else {  // rows 0 and N/2 were transformed as one complex line
-                    for (int c = lt; c < N; c += GI) {
-                        if (GI & 1) s = (c & 1) ? -1.0f : 1.0f;
-                        const float2 a = l0[pad_idx(c)], m = l0[pad_idx((N - c) & (N - 1))];
-                        const float hA = rmul(0.5f * (a.x + m.x), s), hB = rmul(0.5f * (a.y + m.y), s);
-                        mn = hA < mn ? hA : mn; mx = hA > mx ? hA : mx;
-                        mn = hB < mn ? hB : mn; mx = hB > mx ? hB : mx;
+                for (int r = 0; r < R; ++r) {
+                    const int slot = slot_of_column(j + r * St::JN, N);
+                    if constexpr (SLAB) {
+                        const int half = slot >> (LOGN - 1), jj = slot & (H - 1);
+                        const size_t blk = (size_t)8 << (2 * hlog);  // elements per source block: Hl*4*2*Hl
+                        st.v[i * R + r] = src[(size_t)(jj >> hlog) * blk + ((size_t)half << hlog) + (jj & ((1 << hlog) - 1))];
+                    } else {
+                        st.v[i * R + r] = src[slot];
                     }
                 }
-                st.v[0] = make_float2(mn, mx);
-            });
-            ex.commit_minmax(args.minmax + 2 * item.slot);
-        } else {
-            // ---- pack: each transformed line pair yields output rows m' and N-m' -----------------
-            // reference: WSTessendorf.cpp:385-437 (sign, lambda, packing) and :443-455 (normalisation)
-            ex.pdl_wait();
-            ex.pdl_release();
-            const float lambda = args.td[bz].lambda;
-            const float amp = amplitude_of(args.minmax[2 * item.slot], args.minmax[2 * item.slot + 1]);
-            const float inv_amp = rdiv(1.0f, amp);
-            if (bx == 0 && by == 0) {
-                ex.each([&](int tid, ThreadState&) {
-                    if (tid == 0) args.amp_out[item.slot] = amp;
-                });
             }
-            float4* out = (by == 0 ? args.disp : args.norm) + (size_t)item.slot * ((size_t)N * N);
-            ex.each([&](int tid, ThreadState&) {
-                const int ri = tid / GI, lt = tid % GI;
-                const int mp = bx * RI + ri;
-                const float2* l0 = smem + (ri * 2 + 0) * LS;
-                const float2* l1 = l0 + LS;
-                // (-1)^(row+col) is the same for both output rows and every column this thread visits
-                const float s = ((mp + lt) & 1) ? -1.0f : 1.0f;
-                const float sl = rmul(s, lambda);
-                if (mp != 0) {
-                    float4* outA = out + (size_t)mp * N;
-                    float4* outB = out + (size_t)(N - mp) * N;
-                    for (int c = lt; c < N; c += GI) {
-                        const int e = pad_idx(c);
-                        const float2 a0 = l0[e], a1 = l1[e];
-                        const int cm = (N - c) & (N - 1);   // row N-m' is the conjugate mirror of row m'
-                        if (by == 0) {
-                            const float y = rmul(rmul(a0.x, s), inv_amp);
-                            const float x = rmul(sl, a0.y), z = rmul(sl, a1.y);
-                            outA[c] = make_float4(x, y, z, 1.0f);
-                            outB[cm] = make_float4(-x, y, -z, 1.0f);
-                        } else {
-                            const float4 ta = make_float4(s * a0.y, s * a1.y, s * a0.x, s * a1.x);
-                            outA[c] = ta;
-                            outB[cm] = make_float4(-ta.x, -ta.y, ta.z, ta.w);
-                        }
-                    }
-                } else {
-                    // rows 0 and N/2 were transformed as one complex line: separate them
-                    float4* outA = out;
-                    float4* outB = out + (size_t)H * N;
-                    for (int c = lt; c < N; c += GI) {
-                        const int e = pad_idx(c), em = pad_idx((N - c) & (N - 1));
-                        const float2 p0 = l0[e], p1 = l1[e], m0 = l0[em], m1 = l1[em];
-                        const float2 a0 = make_float2(0.5f * (p0.x + m0.x), 0.5f * (p0.y - m0.y));
-                        const float2 a1 = make_float2(0.5f * (p1.x + m1.x), 0.5f * (p1.y - m1.y));
-                        const float2 b0 = make_float2(0.5f * (p0.y + m0.y), -0.5f * (p0.x - m0.x));
-                        const float2 b1 = make_float2(0.5f * (p1.y + m1.y), -0.5f * (p1.x - m1.x));
-                        if (by == 0) {
-                            outA[c] = make_float4(rmul(sl, a0.y), rmul(rmul(a0.x, s), inv_amp), rmul(sl, a1.y), 1.0f);
-                            outB[c] = make_float4(rmul(sl, b0.y), rmul(rmul(b0.x, s), inv_amp), rmul(sl, b1.y), 1.0f);
-                        } else {
-                            outA[c] = make_float4(s * a0.y, s * a1.y, s * a0.x, s * a1.x);
-                            outB[c] = make_float4(s * b0.y, s * b1.y, s * b0.x, s * b1.x);
-                        }
-                    }
+            St::twiddle_dft(args.tw, tid, st);
+            St::store(smem, tid, st);
+        });
+        ex.template sync_group<G, T>(1);
+        if constexpr (Plan<LOGN>::S > 1) RunStages<LOGN, B, 1, R, Exec>::run(ex, smem, args.tw);
+    }
+
+    // ---- K2h: min/max of the height = Re of packed field 0
+    template <class Exec, class Args>
+    static WSO_HD void reduce_heights(Exec& ex, const float2* smem, int bx, int bz, const Args& args) {
+        const BatchItem item = args.items[bz];
+        const int hlog = hl_log(args);
+        ex.each([&](int tid, ThreadState& st) {
+            float mn = kInitMin, mx = kInitMax;
+            const int ri = tid / GI, lt = tid % GI;
+            const int mp = (SLAB ? (args.slab_rank << hlog) : 0) + bx * RI + ri;
+            const float2* l0 = smem + ri * LS;
+            // (-1)^(row+col): loop invariant when the column stride GI is even (N >= 32)
+            float s = ((mp + lt) & 1) ? -1.0f : 1.0f;
+            if (mp != 0) {
+                for (int c = lt; c < N; c += GI) {
+                    if (GI & 1) s = ((mp + c) & 1) ? -1.0f : 1.0f;
+                    const float h = rmul(l0[pad_idx(c)].x, s);
+                    mn = h < mn ? h : mn;
+                    mx = h > mx ? h : mx;
                 }
+            } else {  // rows 0 and N/2 were transformed as one complex line
+                for (int c = lt; c < N; c += GI) {
+                    if (GI & 1) s = (c & 1) ? -1.0f : 1.0f;
+                    const float2 a = l0[pad_idx(c)], m = l0[pad_idx((N - c) & (N - 1))];
+                    const float hA = rmul(0.5f * (a.x + m.x), s), hB = rmul(0.5f * (a.y + m.y), s);
+                    mn = hA < mn ? hA : mn; mx = hA > mx ? hA : mx;
+                    mn = hB < mn ? hB : mn; mx = hB > mx ? hB : mx;
+                }
+            }
+            st.v[0] = make_float2(mn, mx);
+        });
+        ex.commit_minmax(args.minmax + 2 * item.slot);
+    }
+
+    // ---- K2 pack: each transformed line pair (l0, l1) yields output rows A = m' and B = N-m' (rows 0 and N/2 for
+    // m' = 0).  rows: bit 0 = write row A, bit 1 = write row B.
+    // reference: WSTessendorf.cpp:385-437 (sign, lambda, packing) and :443-455 (normalisation)
+    static WSO_HD void pack_item(const float2* l0, const float2* l1, int mp, float4* outA, float4* outB, int by,
+                                 float lambda, float inv_amp, int lt, int stride, int rows) {
+        // (-1)^(row+col) is the same for both output rows and every column this thread visits (stride is even)
+        const float s = ((mp + lt) & 1) ? -1.0f : 1.0f;
+        const float sl = rmul(s, lambda);
+        if (mp != 0) {
+            for (int c = lt; c < N; c += stride) {
+                const int e = pad_idx(c);
+                const float2 a0 = l0[e], a1 = l1[e];
+                const int cm = (N - c) & (N - 1);   // row N-m' is the conjugate mirror of row m'
+                if (by == 0) {
+                    const float y = rmul(rmul(a0.x, s), inv_amp);
+                    const float x = rmul(sl, a0.y), z = rmul(sl, a1.y);
+                    if (rows & 1) outA[c] = make_float4(x, y, z, 1.0f);
+                    if (rows & 2) outB[cm] = make_float4(-x, y, -z, 1.0f);
+                } else {
+                    const float4 ta = make_float4(s * a0.y, s * a1.y, s * a0.x, s * a1.x);
+                    if (rows & 1) outA[c] = ta;
+                    if (rows & 2) outB[cm] = make_float4(-ta.x, -ta.y, ta.z, ta.w);
+                }
+            }
+        } else {
+            // rows 0 and N/2 were transformed as one complex line: separate them
+            for (int c = lt; c < N; c += stride) {
+                const int e = pad_idx(c), em = pad_idx((N - c) & (N - 1));
+                const float2 p0 = l0[e], p1 = l1[e], m0 = l0[em], m1 = l1[em];
+                const float2 a0 = make_float2(0.5f * (p0.x + m0.x), 0.5f * (p0.y - m0.y));
+                const float2 a1 = make_float2(0.5f * (p1.x + m1.x), 0.5f * (p1.y - m1.y));
+                const float2 b0 = make_float2(0.5f * (p0.y + m0.y), -0.5f * (p0.x - m0.x));
+                const float2 b1 = make_float2(0.5f * (p1.y + m1.y), -0.5f * (p1.x - m1.x));
+                if (by == 0) {
+                    if (rows & 1) outA[c] = make_float4(rmul(sl, a0.y), rmul(rmul(a0.x, s), inv_amp), rmul(sl, a1.y), 1.0f);
+                    if (rows & 2) outB[c] = make_float4(rmul(sl, b0.y), rmul(rmul(b0.x, s), inv_amp), rmul(sl, b1.y), 1.0f);
+                } else {
+                    if (rows & 1) outA[c] = make_float4(s * a0.y, s * a1.y, s * a0.x, s * a1.x);
+                    if (rows & 2) outB[c] = make_float4(s * b0.y, s * b1.y, s * b0.x, s * b1.x);
+                }
+            }
+        }
+    }
+
+    // smem_peer: the partner CTA's line (PAIR only; distributed shared memory on the device)
+    template <class Exec, class Args>
+    static WSO_HD void pack(Exec& ex, const float2* smem, const float2* smem_peer, int bx, int by, int bz, int crank,
+                            const Args& args) {
+        const BatchItem item = args.items[bz];
+        ex.pdl_wait();
+        ex.pdl_release();
+        const float lambda = args.td[bz].lambda;
+        const float amp = amplitude_of(args.minmax[2 * item.slot], args.minmax[2 * item.slot + 1]);
+        const float inv_amp = rdiv(1.0f, amp);
+        if (bx == 0 && by == 0 && crank == 0) {
+            ex.each([&](int tid, ThreadState&) {
+                if (tid == 0) args.amp_out[item.slot] = amp;
             });
+        }
+        const int hlog = hl_log(args);
+        const size_t rows_per_slot = SLAB ? ((size_t)2 << hlog) : (size_t)N;
+        float4* out = (by == 0 ? args.disp : args.norm) + (size_t)item.slot * (rows_per_slot * N);
+        ex.each([&](int tid, ThreadState&) {
+            const int ri = tid / GI, lt = tid % GI;
+            const int ml = bx * RI + ri;
+            const int mp = (SLAB ? (args.slab_rank << hlog) : 0) + ml;
+            const float2 *l0, *l1;
+            int rows = 3;
+            if constexpr (PAIR) {
+                l0 = crank == 0 ? smem : smem_peer;
+                l1 = crank == 0 ? smem_peer : smem;
+                rows = crank == 0 ? 1 : 2;
+            } else {
+                l0 = smem + (ri * 2 + 0) * LS;
+                l1 = l0 + LS;
+            }
+            float4* outA = out + (size_t)(SLAB ? ml : mp) * N;
+            float4* outB = out + (size_t)(SLAB ? (1 << hlog) + ml : (mp == 0 ? H : N - mp)) * N;
+            pack_item(l0, l1, mp, outA, outB, by, lambda, inv_amp, lt, GI, rows);
+        });
+    }
+
+    // one CTA holds whole row items (every size whose line pair fits shared memory)
+    template <class Exec, class Args>
+    static WSO_HD void run(Exec& ex, float2* smem, int bx, int by, int bz, const Args& args) {
+        static_assert(!PAIR, "cluster pairs are driven phase by phase (transform / cluster barrier / pack)");
+        transform(ex, smem, bx, by, bz, 0, args);
+        if constexpr (HEIGHT_ONLY) {
+            reduce_heights(ex, smem, bx, bz, args);
+        } else {
+            // the pack phase of a row item reads both of its lines: barrier over that pair of line groups
+            ex.template sync_group<GI, T>(1 + (G > 32 ? B : 0));
+            pack(ex, smem, nullptr, bx, by, bz, 0, args);
         }
     }
 };

@@ -18,4 +18,10 @@ cudaError_t launch_compute_waves(int logn, const LaunchArgs& args, int n_items, 
                                  bool first_use, cudaEvent_t* ev);
 int kernels_per_launch();
 
+// Slab-decomposed path (one grid over several devices).  phase 0: K1 on this device's column pairs,
+// 1: K2h on its row items, 2: K2 (pair = force the two-CTA cluster variant; always used when a line pair exceeds
+// one SM's shared memory).
+cudaError_t launch_slab_phase(int logn, int phase, const LaunchArgsT<1>& args, bool pair, cudaStream_t stream);
+bool slab_size_supported(int logn);
+
 }  // namespace wso
