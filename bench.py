@@ -47,6 +47,11 @@ WORKLOADS = {
                desc="BASELINE configs[2]: 2048x2048 tile, all maps, frames t_i = i*0.05 s, 32 frames per step per GPU"),
     "c4": dict(n=512, L=1000.0, seed=1000, frames=64, tiles=64, dt=0.0,
                desc="BASELINE configs[3]: 64 independent 512x512 tiles (wind angle 2*pi*j/64, V=5+0.5j, seed 1000+j), t=10"),
+    # one grid over ALL ranks (strong scaling): slab-decomposed transform with one exchange step (run_slab below)
+    "c5": dict(n=16384, L=32000.0, seed=7, frames=1, tiles=1, dt=0.05, t0=10.0,
+               desc="BASELINE configs[4]: single 16384x16384 patch, slab-decomposed over the ranks, t = 10 + 0.05*k"),
+    "c5s": dict(n=2048, L=4000.0, seed=7, frames=1, tiles=1, dt=0.05, t0=10.0,
+                desc="2048x2048 patch through the slab-decomposed path (the size the slab parity tests use)"),
 }
 
 
@@ -162,6 +167,8 @@ def tile_params(wl, j):
 
 def step_times(wl, step):
     f = wl["frames"]
+    if "t0" in wl:
+        return np.array([wl["t0"] + wl["dt"] * step], np.float32), None
     if wl["tiles"] > 1:
         return np.full(f, 10.0, np.float32), np.arange(f, dtype=np.uint32) % wl["tiles"]
     i0 = step * f
@@ -171,6 +178,10 @@ def step_times(wl, step):
 def run_reference_arm(args, wl, rank, world):
     if rank != 0:
         return
+    scale = 1.0
+    if wl["n"] > 4096:   # the reference needs ~33 GB and minutes per 16384^2 frame: time 4096^2 and scale by points
+        scale = (wl["n"] / 4096) ** 2
+        wl = dict(wl, n=4096, L=wl["L"] * 4096 / wl["n"], desc=wl["desc"] + f" [CPU arm timed at 4096^2, value / {scale:.0f}]")
     kind, label, cores, make = cpu_reference_model(wl)
     # bounded sample per step so the whole run ends within minutes
     sample = {512: 8, 1024: 3, 2048: 1}.get(wl["n"], 1)
@@ -185,7 +196,7 @@ def run_reference_arm(args, wl, rank, world):
     for k in range(args.steps):
         one_step(args.warmup + k)
     dt = time.perf_counter() - t0
-    value = sample * args.steps / dt
+    value = sample * args.steps / dt / scale
     line = {
         "impl": "reference", "metric": "ocean tile-frames/s", "value": value, "unit": "tile-frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
@@ -219,6 +230,160 @@ def measure_cpu_baseline(wl, budget_s=12.0):
 
 
 # ----------------------------------------------------------------------------------------------------
+def run_slab(args, wl, rank, world, local_rank):
+    """BASELINE configs[4]: ONE N x N tile-frame per step over all ranks (strong scaling).  Per step: K1 on the local
+    column pairs -> exchange (NCCL all-to-all, or --slab-fused: peer stores inside K1 + an ordering collective) ->
+    K2h -> 2-float all-reduce -> K2 on the local rows."""
+    import torch
+    import torch.distributed as dist
+    import watersurfacerendering_b200 as W
+    from watersurfacerendering_b200 import _lib as L
+    from watersurfacerendering_b200.slab import SlabBackend, SlabOcean
+    n = wl["n"]
+    stream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(stream)
+    t_prep = time.perf_counter()
+    b = SlabBackend(n, wl["L"], rank, world, local_rank)
+    b.set_stream(stream.cuda_stream)
+    b.prepare_counter(wl["seed"])
+    t_prep = time.perf_counter() - t_prep
+    ocean = SlabOcean(b, fused=bool(args.slab_fused))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        tt = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    tk = lambda k: wl["t0"] + wl["dt"] * k
+    for k in range(args.warmup):
+        ocean.compute(tk(k))
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for k in range(args.warmup, args.warmup + args.steps):
+        ocean.compute(tk(k))
+    e1.record(stream)
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    amp, mn, mx = b.read_heights()
+
+    # ---- per-phase device time (events around every phase; same steps again)
+    names = ["K1", "exchange", "K2h", "allreduce", "K2"]
+    evs = []
+    for k in range(args.warmup, args.warmup + args.steps):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        ev[0].record(stream)
+        b.pass1(tk(k))
+        ev[1].record(stream)
+        if world > 1 and not ocean.fused:
+            dist.all_to_all_single(b.recv, b.send)
+        elif world > 1:
+            dist.all_reduce(ocean._scratch())
+        ev[2].record(stream)
+        b.heights()
+        ev[3].record(stream)
+        if world > 1:
+            v = torch.stack((b.minmax[0], -b.minmax[1]))
+            dist.all_reduce(v, op=dist.ReduceOp.MIN)
+            b.minmax[0] = v[0]
+            b.minmax[1] = -v[1]
+        ev[4].record(stream)
+        b.pass2()
+        ev[5].record(stream)
+        evs.append(ev)
+    barrier()
+    per_step = {nm: [ev[i].elapsed_time(ev[i + 1]) for ev in evs] for i, nm in enumerate(names)}
+    # median over steps (a collective occasionally absorbs a host-side hiccup of the other rank), max over ranks
+    phase_ms = {nm: max_over_ranks(float(np.median(per_step[nm]))) for nm in names}
+
+    # ---- end to end: the local rows of both maps to pinned host memory inside the timed region
+    rows = 2 * b.hl
+    hd, hn = W.PinnedBuffer((rows, n, 4)), W.PinnedBuffer((rows, n, 4))
+    import ctypes as C
+    def e2e_step(k):
+        ocean.compute(tk(k))
+        L.check_slab(b._lib.wso_slab_copy_rows(b._h, 0, hd.array.ctypes.data_as(C.c_void_p)), b._h)
+        L.check_slab(b._lib.wso_slab_copy_rows(b._h, 1, hn.array.ctypes.data_as(C.c_void_p)), b._h)
+    e2e_step(0)
+    barrier()
+    t0 = time.perf_counter()
+    ne = max(1, min(args.steps, 3))
+    for k in range(ne):
+        e2e_step(k + 1)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+
+    peak, peak_src = measured_peak()
+    pts = float(n) * n
+    ms_step = ms / args.steps
+    dom = max(("K1", "K2h", "K2"), key=lambda nm: phase_ms[nm])
+    dom_bytes = BYTES_PER_POINT[dom] * pts / world      # per launch = this rank's share of one tile-frame
+    nvl_bytes_per_gpu = 16.0 * pts / world * (world - 1) / world   # W blocks that leave each GPU
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        try:
+            ns = min(n, 4096)
+            wl_s = dict(wl, n=ns, L=wl["L"] * ns / n, tiles=1, frames=1)
+            cb = measure_cpu_baseline(wl_s, budget_s=10.0)
+            scale = (n / ns) ** 2
+            cpu = {"value": cb["value"] / scale, "unit": "tile-frames/s", "cores": cb["cores"], "kind": cb["kind"],
+                   "sample": f"{cb['sample']}; measured at {ns}^2 and divided by {scale:.0f} (points ratio) to stand "
+                             f"for {n}^2 - the reference code needs ~33 GB and minutes per frame at 16384^2"}
+        except Exception as ex:
+            cpu = {"value": None, "unit": "tile-frames/s", "cores": 0, "kind": "unavailable", "sample": repr(ex)}
+    if rank == 0:
+        line = {
+            "metric": "ocean tile-frames/s", "value": args.steps / (ms * 1e-3), "unit": "tile-frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "tile_size": n, "frames_per_step": 1,
+                       "exchange": "fused peer stores in K1 (NVLink, CUDA IPC)" if ocean.fused else
+                                   ("NCCL all_to_all_single" if world > 1 else "none (one rank)"),
+                       "l2": f"one tile-frame moves {108 * pts / 1e9:.1f} GB >> 126 MB L2",
+                       "parallelism": f"slab decomposition x{world}: 1 exchange + 1 two-float all-reduce per tile-frame",
+                       "prepare_s": t_prep},
+            "us_per_tile_frame": ms_step * 1e3,
+            "e2e": {"value": ne / e2e_s, "unit": "tile-frames/s", "h2d_bytes_per_step": 4,
+                    "d2h_bytes_per_step": int(2 * 16 * rows * n), "api": "SlabOcean.compute + wso_slab_copy_rows (pinned)"},
+            "gpu_launches": int(3 * args.steps),
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": dom_bytes / (phase_ms[dom] * 1e-3) / 1e9,
+                         "peak": peak, "unit": "GB/s",
+                         "frac": dom_bytes / (phase_ms[dom] * 1e-3) / 1e9 / peak, "peak_source": peak_src, "traffic": None,
+                         "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": phase_ms[dom],
+                         "phase_ms": phase_ms, "phase_ms_per_step_rank0": per_step,
+                         "whole_path_gbs_per_gpu": sum(BYTES_PER_POINT.values()) * pts / world / (ms_step * 1e-3) / 1e9,
+                         "survey_model_whole_path_gbs_per_gpu": 108.0 * pts / world / (ms_step * 1e-3) / 1e9,
+                         "nvlink": None if world == 1 else {
+                             "bytes_out_per_gpu": nvl_bytes_per_gpu, "exchange_ms": phase_ms["exchange"],
+                             "achieved_gbs_per_dir": nvl_bytes_per_gpu / (phase_ms["exchange"] * 1e-3) / 1e9
+                             if not ocean.fused else nvl_bytes_per_gpu / (phase_ms["K1"] * 1e-3) / 1e9,
+                             "peak_gbs_per_dir": 770.0, "peak_source": "B200_PROFILING.md measured peer copy"}},
+            "heights": {"amplitude": float(amp), "min": float(mn), "max": float(mx)},
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    hd.close()
+    hn.close()
+    b.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -228,6 +393,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-frames", type=int, default=0, help="tile-frames per e2e step (default: min(frames, 24))")
+    ap.add_argument("--slab-fused", type=int, default=0, help="c5: exchange by peer stores inside K1 instead of all-to-all")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
@@ -249,6 +415,10 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    if args.workload in ("c5", "c5s"):
+        run_slab(args, wl, rank, world, local_rank)
+        return
 
     import watersurfacerendering_b200 as W
     from watersurfacerendering_b200 import sharding

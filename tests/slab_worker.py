@@ -15,7 +15,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=2048)
+    ap.add_argument("--size", type=int, default=2048)
     ap.add_argument("--fused", type=int, default=0)
     ap.add_argument("--pair", type=int, default=0)
     ap.add_argument("--out", default="")
@@ -26,7 +26,7 @@ def main():
     from conftest import SCALAR_REL_TOL, assert_maps_close
     from oracle import port as P
     from watersurfacerendering_b200.slab import SlabBackend, SlabOcean
-    n = a.n
+    n = a.size
     p = P.OceanParams(tile_size=n, tile_length=1000.0 * n / 512)
     o = P.PortOracle(p)
     rng = np.random.default_rng(n)

@@ -178,7 +178,7 @@ def test_slab_two_gpus_vs_oracle(fused, tmp_path):
         pytest.skip("needs >= 2 GPUs")
     out = tmp_path / "res.txt"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "slab_worker.py"), "--n", "2048",
+           "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "slab_worker.py"), "--size", "2048",
            "--fused", str(fused), "--out", str(out)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
