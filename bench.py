@@ -245,7 +245,9 @@ def run_slab(args, wl, rank, world, local_rank):
     t_prep = time.perf_counter()
     b = SlabBackend(n, wl["L"], rank, world, local_rank)
     b.set_stream(stream.cuda_stream)
-    b.prepare_counter(wl["seed"])
+    t_prep_kernel = time.perf_counter()
+    b.prepare_counter_device(wl["seed"])   # Prepare() on the device: this rank's column pairs only
+    t_prep_kernel = time.perf_counter() - t_prep_kernel
     t_prep = time.perf_counter() - t_prep
     ocean = SlabOcean(b, fused=bool(args.slab_fused))
 
@@ -354,7 +356,7 @@ def run_slab(args, wl, rank, world, local_rank):
                                    ("NCCL all_to_all_single" if world > 1 else "none (one rank)"),
                        "l2": f"one tile-frame moves {108 * pts / 1e9:.1f} GB >> 126 MB L2",
                        "parallelism": f"slab decomposition x{world}: 1 exchange + 1 two-float all-reduce per tile-frame",
-                       "prepare_s": t_prep},
+                       "prepare_s": t_prep, "prepare_device_kernel_s": t_prep_kernel},
             "us_per_tile_frame": ms_step * 1e3,
             "e2e": {"value": ne / e2e_s, "unit": "tile-frames/s", "h2d_bytes_per_step": 4,
                     "d2h_bytes_per_step": int(2 * 16 * rows * n), "api": "SlabOcean.compute + wso_slab_copy_rows (pinned)"},

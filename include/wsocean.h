@@ -87,6 +87,17 @@ WSO_API int wso_prepare(wso_ctx* ctx, uint32_t tile, int reseed, unsigned seed);
 /* Same, with a caller-supplied Gaussian array xi: N*N complex<float> (re,im), row-major [m][n]
  * (the array ComputeGaussRandomArray returns, WSTessendorf.cpp:87-103). */
 WSO_API int wso_prepare_gauss(wso_ctx* ctx, uint32_t tile, const float* xi);
+/* Prepare() ON THE DEVICE (replaces the CPU passes ComputeWaveVectors + ComputeBaseWaveHeightField,
+ * WSTessendorf.cpp:60-85, 105-148, with PhillipsSpectrum / BaseWaveHeightFT / QDispersion, WSTessendorf.h:237-297):
+ * one kernel builds the spectrum records straight in device memory from the uploaded Gaussian array xi (same
+ * layout as above).  Dispersion, 1/|k| and layout are bit-identical to wso_prepare_gauss; amplitudes agree to
+ * 1 ulp (the two exp() are evaluated in float64 on the device).  No host copy of h0 is kept: wso_export_h0 reads
+ * the records back. */
+WSO_API int wso_prepare_gauss_device(wso_ctx* ctx, uint32_t tile, const float* xi);
+/* Same, the Gaussian array drawn in the kernel from the counter-based generator (seed, m*N+n) - a reproducible
+ * stand-in for the reference's serial rand() stream (ComputeGaussRandomArray, WSTessendorf.cpp:87-103); the host
+ * build of the same generator is wso_counter_h0. */
+WSO_API int wso_prepare_counter(wso_ctx* ctx, uint32_t tile, uint64_t seed);
 /* Import / export h0 in the reference's own layout: N*N records, row-major [m][n]
  * (m_BaseWaveHeights, WSTessendorf.h:197).  Import replaces the spectrum of a tile whose parameters
  * (tile_length in particular) were set beforehand; this is also the checkpoint/restore mechanism. */
@@ -163,6 +174,8 @@ WSO_API int wso_slab_destroy(wso_slab* s);
  * (WSTessendorf.cpp:105-148).  wso_counter_h0 evaluates the same records for rows [m0, m0+rows) - for checkers. */
 WSO_API int wso_slab_import_h0(wso_slab* s, const wso_h0_record* h0_full);
 WSO_API int wso_slab_prepare_counter(wso_slab* s, uint64_t seed);
+/* the same spectrum built by the device Prepare kernel (this rank's column pairs only; no host pass) */
+WSO_API int wso_slab_prepare_counter_device(wso_slab* s, uint64_t seed);
 WSO_API int wso_counter_h0(const wso_params* p, uint64_t seed, uint32_t m0, uint32_t rows, wso_h0_record* out);
 WSO_API int wso_slab_set_lambda(wso_slab* s, float lambda);
 WSO_API int wso_slab_set_stream(wso_slab* s, void* cuda_stream);

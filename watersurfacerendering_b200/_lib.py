@@ -56,6 +56,8 @@ SYMBOLS = {
     "wso_set_lambda": (_int, [_vp, _u32, _f32]),
     "wso_prepare": (_int, [_vp, _u32, _int, C.c_uint]),
     "wso_prepare_gauss": (_int, [_vp, _u32, _vp]),
+    "wso_prepare_gauss_device": (_int, [_vp, _u32, _vp]),
+    "wso_prepare_counter": (_int, [_vp, _u32, C.c_uint64]),
     "wso_import_h0": (_int, [_vp, _u32, _vp]),
     "wso_export_h0": (_int, [_vp, _u32, _vp]),
     "wso_compute": (_int, [_vp, _f32, C.POINTER(_f32)]),
@@ -77,6 +79,7 @@ SYMBOLS = {
     "wso_slab_destroy": (_int, [_vp]),
     "wso_slab_import_h0": (_int, [_vp, _vp]),
     "wso_slab_prepare_counter": (_int, [_vp, C.c_uint64]),
+    "wso_slab_prepare_counter_device": (_int, [_vp, C.c_uint64]),
     "wso_counter_h0": (_int, [_pp, C.c_uint64, _u32, _u32, _vp]),
     "wso_slab_set_lambda": (_int, [_vp, _f32]),
     "wso_slab_set_stream": (_int, [_vp, _vp]),

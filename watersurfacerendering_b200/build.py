@@ -17,7 +17,8 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 INCLUDE = os.path.join(ROOT, "include")
 LIB_PATH = os.path.join(PKG_DIR, "libwsocean.so")
 
-SOURCES = ["wso_kernels.cu", "wso_slab_kernels.cu", "wso_api.cu", "wso_slab.cu", "wso_host_prepare.cpp"]
+SOURCES = ["wso_kernels.cu", "wso_slab_kernels.cu", "wso_prepare_kernels.cu", "wso_api.cu", "wso_slab.cu",
+           "wso_host_prepare.cpp"]
 HEADERS = ["wso_device.cuh", "wso_kernels.cuh", "wso_launch.h", "wso_host_prepare.h"]
 
 NVCC_FLAGS = [

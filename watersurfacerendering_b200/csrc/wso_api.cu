@@ -317,6 +317,50 @@ int enqueue_chunk(wso_ctx* c, uint32_t n_items, const uint32_t* tiles, const flo
     return WSO_OK;
 }
 
+// Prepare() on the device: one kernel builds both record arrays of the tile from a Gaussian array
+// already in device memory (d_xi) or from the counter-based generator (d_xi == NULL).
+int prepare_on_device(wso_ctx* c, uint32_t tile, const float2* d_xi, uint64_t seed) {
+    const uint32_t n = c->n;
+    Tile& tl = c->tiles[tile];
+    const wso::DerivedParams d = wso::derive_params(tl.params);
+    std::vector<float> kv;
+    wso::host_wave_numbers(n, tl.params.tile_length, kv);
+    // largest multiple j of the base frequency: the wave vector of index (0,0) has the largest |k|, and
+    // floor(sqrt(g k)/omega0) is monotone in |k| (same fp32 operations as the kernel)
+    const float kmax = std::sqrt(kv[0] * kv[0] + kv[0] * kv[0]);
+    const float jf = std::floor(std::sqrt(9.81f * kmax) / d.base_freq);
+    if (!(d.base_freq > 0.0f) || !(jf >= 0.0f && jf < (float)wso::kMaxTable))
+        return fail(c, WSO_ERR_INVALID_ARG, "device Prepare: dispersion table would exceed 1024 entries (use wso_prepare)");
+    wso::PrepareArgs a;
+    a.h0 = c->d_h0 + (size_t)n * n * tile;
+    a.hs = c->d_hs + ((size_t)n * n / 2) * tile;
+    a.kv = c->d_kv + (size_t)n * tile;
+    a.xi = d_xi;
+    a.seed_mixed = wso::counter_seed_mix(seed);
+    a.n = (int)n;
+    a.j0 = 0;
+    a.wind_x = d.wind_x;
+    a.wind_y = d.wind_y;
+    a.omega0 = d.base_freq;
+    a.phillips_const = tl.params.phillips_const;
+    a.damping = tl.params.damping;
+    a.inv_sqrt2 = 1.0f / std::sqrt(2.0f);
+    const float Lw = d.wind_speed * d.wind_speed / 9.81f;
+    a.Lw2 = Lw * Lw;
+    WSO_CUDA(c, cudaSetDevice(c->device));
+    WSO_CUDA(c, cudaMemcpyAsync(c->d_kv + (size_t)n * tile, kv.data(), sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
+    WSO_CUDA(c, wso::launch_prepare(a, (int)(n / 2), c->stream));
+    WSO_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->launches += 1;
+    c->h_tiles[tile].omega0 = d.base_freq;
+    c->h_tiles[tile].table_len = (int)jf + 1;
+    c->h_tiles[tile].use_pairs = 1;
+    tl.h0.clear();  // the records live on the device only; wso_export_h0 reads them back
+    tl.prepared = tl.params;
+    tl.is_prepared = true;
+    return WSO_OK;
+}
+
 int check_batch(wso_ctx* c, uint32_t n, const uint32_t* tiles, const float* t, uint32_t first_slot) {
     if (!c) return WSO_ERR_INVALID_ARG;
     if (!t) return fail(c, WSO_ERR_INVALID_ARG, "t is NULL");
@@ -458,6 +502,30 @@ int wso_prepare_gauss(wso_ctx* c, uint32_t tile, const float* xi) {
     return upload_h0(c, tile, tl.h0.data());
 }
 
+int wso_prepare_gauss_device(wso_ctx* c, uint32_t tile, const float* xi) {
+    int rc = begin_prepare(c, tile);
+    if (rc != WSO_OK) return rc;
+    if (!xi) return fail(c, WSO_ERR_INVALID_ARG, "xi is NULL");
+    const size_t bytes = sizeof(float2) * (size_t)c->n * c->n;
+    float2* d_xi = nullptr;
+    WSO_CUDA(c, cudaSetDevice(c->device));
+    WSO_CUDA(c, cudaMalloc(&d_xi, bytes));
+    cudaError_t e = cudaMemcpyAsync(d_xi, xi, bytes, cudaMemcpyHostToDevice, c->stream);
+    if (e != cudaSuccess) {
+        cudaFree(d_xi);
+        return fail_cuda(c, e, "cudaMemcpyAsync(xi)");
+    }
+    rc = prepare_on_device(c, tile, d_xi, 0);
+    cudaFree(d_xi);
+    return rc;
+}
+
+int wso_prepare_counter(wso_ctx* c, uint32_t tile, uint64_t seed) {
+    int rc = begin_prepare(c, tile);
+    if (rc != WSO_OK) return rc;
+    return prepare_on_device(c, tile, nullptr, seed);
+}
+
 int wso_import_h0(wso_ctx* c, uint32_t tile, const wso_h0_record* h0) {
     int rc = begin_prepare(c, tile);
     if (rc != WSO_OK) return rc;
@@ -467,9 +535,23 @@ int wso_import_h0(wso_ctx* c, uint32_t tile, const wso_h0_record* h0) {
 
 int wso_export_h0(const wso_ctx* c, uint32_t tile, wso_h0_record* h0) {
     if (!c || !h0 || tile >= c->max_tiles) return WSO_ERR_INVALID_ARG;
-    if (!c->tiles[tile].is_prepared) return WSO_ERR_NOT_PREPARED;
-    std::memcpy(h0, c->tiles[tile].h0.data(), sizeof(wso_h0_record) * c->tiles[tile].h0.size());
-    return WSO_OK;
+    const Tile& tl = c->tiles[tile];
+    if (!tl.is_prepared) return WSO_ERR_NOT_PREPARED;
+    if (!tl.h0.empty()) {
+        std::memcpy(h0, tl.h0.data(), sizeof(wso_h0_record) * tl.h0.size());
+        return WSO_OK;
+    }
+    // prepared on the device: rebuild the reference records from the device arrays
+    static_assert(sizeof(wso_h0_record) == 20, "reference BaseWaveHeight is 5 floats");
+    const size_t n2 = (size_t)c->n * c->n;
+    float* d_out = nullptr;
+    if (cudaSetDevice(c->device) != cudaSuccess || cudaMalloc(&d_out, n2 * 20) != cudaSuccess) return WSO_ERR_CUDA;
+    const TileDev& td = c->h_tiles[tile];
+    cudaError_t e = wso::launch_export_records(td.h0, d_out, (int)c->n, td.omega0, td.table_len > 0, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h0, d_out, n2 * 20, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_out);
+    return e == cudaSuccess ? WSO_OK : WSO_ERR_CUDA;
 }
 
 int wso_compute_batch(wso_ctx* c, uint32_t n, const uint32_t* tiles, const float* t, uint32_t first_slot) {

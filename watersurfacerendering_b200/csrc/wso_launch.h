@@ -1,6 +1,7 @@
 // wso_launch.h — host-side launch interface of the kernels in wso_kernels.cu.
 #pragma once
 #include <cuda_runtime.h>
+#include <stdint.h>
 
 namespace wso {
 
@@ -23,5 +24,21 @@ int kernels_per_launch();
 // one SM's shared memory).
 cudaError_t launch_slab_phase(int logn, int phase, const LaunchArgsT<1>& args, bool pair, cudaStream_t stream);
 bool slab_size_supported(int logn);
+
+// Prepare() on the device (wso_prepare_kernels.cu).  One launch builds the per-point records
+// h0[jl][half][m] and the pair-summed records hs[jl][i][2] of the column pairs j0 .. j0+n_pairs-1.
+struct PrepareArgs {
+    float4* h0;
+    float4* hs;
+    const float* kv;      // [n] wave numbers (device)
+    const float2* xi;     // [n][n] Gaussian array in the reference's order (device), or NULL: counter-based
+    uint64_t seed_mixed;  // counter_seed_mix(seed)
+    int n, j0;
+    float wind_x, wind_y, omega0, phillips_const, damping, inv_sqrt2, Lw2;
+};
+cudaError_t launch_prepare(const PrepareArgs& a, int n_pairs, cudaStream_t stream);
+// device records of a whole (non-slab) tile -> reference 20-byte records [m][n] in out20 (device, 5 floats each)
+cudaError_t launch_export_records(const float4* h0, float* out20, int n, float omega0, bool table, cudaStream_t stream);
+uint64_t counter_seed_mix(uint64_t seed);
 
 }  // namespace wso

@@ -272,6 +272,48 @@ int wso_slab_prepare_counter(wso_slab* s, uint64_t seed) {
     });
 }
 
+int wso_slab_prepare_counter_device(wso_slab* s, uint64_t seed) {
+    if (!s) return WSO_ERR_INVALID_ARG;
+    const uint32_t n = s->n;
+    const wso::DerivedParams d = wso::derive_params(s->params);
+    std::vector<float> kv;
+    wso::host_wave_numbers(n, s->params.tile_length, kv);
+    const float kmax = std::sqrt(kv[0] * kv[0] + kv[0] * kv[0]);
+    const float jf = std::floor(std::sqrt(9.81f * kmax) / d.base_freq);
+    if (!(d.base_freq > 0.0f) || !(jf >= 0.0f && jf < (float)wso::kMaxTable))
+        return sfail(s, WSO_ERR_INVALID_ARG, "slab path needs a dispersion table of at most 1024 entries");
+    wso::PrepareArgs a;
+    a.h0 = s->d_h0;
+    a.hs = s->d_hs;
+    a.kv = s->d_kv;
+    a.xi = nullptr;
+    a.seed_mixed = wso::counter_seed_mix(seed);
+    a.n = (int)n;
+    a.j0 = (int)(s->rank * s->hl);
+    a.wind_x = d.wind_x;
+    a.wind_y = d.wind_y;
+    a.omega0 = d.base_freq;
+    a.phillips_const = s->params.phillips_const;
+    a.damping = s->params.damping;
+    a.inv_sqrt2 = 1.0f / std::sqrt(2.0f);
+    const float Lw = d.wind_speed * d.wind_speed / 9.81f;
+    a.Lw2 = Lw * Lw;
+    SLAB_CUDA(s, cudaSetDevice(s->device));
+    SLAB_CUDA(s, cudaMemcpyAsync(s->d_kv, kv.data(), sizeof(float) * n, cudaMemcpyHostToDevice, s->stream));
+    SLAB_CUDA(s, wso::launch_prepare(a, (int)s->hl, s->stream));
+    SLAB_CUDA(s, cudaStreamSynchronize(s->stream));
+    s->td.h0 = s->d_h0;
+    s->td.hs = s->d_hs;
+    s->td.kv = s->d_kv;
+    s->td.lambda = s->params.lambda;
+    s->td.omega0 = d.base_freq;
+    s->td.table_len = (int)jf + 1;
+    s->td.use_pairs = 1;
+    s->td.j0 = (int)(s->rank * s->hl);
+    s->prepared = true;
+    return WSO_OK;
+}
+
 int wso_counter_h0(const wso_params* p, uint64_t seed, uint32_t m0, uint32_t rows, wso_h0_record* out) {
     if (!p || !out) return WSO_ERR_INVALID_ARG;
     wso_params q = *p;

@@ -78,6 +78,10 @@ class SlabBackend:
     def prepare_counter(self, seed: int):
         L.check_slab(self._lib.wso_slab_prepare_counter(self._h, int(seed)), self._h)
 
+    def prepare_counter_device(self, seed: int):
+        """The same spectrum, built by the device Prepare kernel (this rank's column pairs only)."""
+        L.check_slab(self._lib.wso_slab_prepare_counter_device(self._h, int(seed)), self._h)
+
     def set_lambda(self, lam: float):
         L.check_slab(self._lib.wso_slab_set_lambda(self._h, float(lam)), self._h)
 

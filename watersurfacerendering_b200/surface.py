@@ -154,6 +154,16 @@ class WSTessendorf:
         xi = np.ascontiguousarray(xi, np.complex64).reshape(n, n)
         L.check(self._lib.wso_prepare_gauss(self._h, tile, _ptr(xi)), self._h)
 
+    def PrepareWithGaussOnDevice(self, xi: np.ndarray, tile: int = 0):
+        """Prepare() with the spectrum built by the device kernel (wso_prepare_gauss_device) from the Gaussian array."""
+        n = self.GetTileSize(tile)
+        xi = np.ascontiguousarray(xi, np.complex64).reshape(n, n)
+        L.check(self._lib.wso_prepare_gauss_device(self._h, tile, _ptr(xi)), self._h)
+
+    def PrepareCounterOnDevice(self, seed: int, tile: int = 0):
+        """Prepare() entirely on the device: counter-based Gaussian array + spectrum (wso_prepare_counter)."""
+        L.check(self._lib.wso_prepare_counter(self._h, tile, int(seed)), self._h)
+
     def ImportH0(self, h0: np.ndarray, tile: int = 0):
         n = self.GetTileSize(tile)
         if h0.dtype != H0_DTYPE:
