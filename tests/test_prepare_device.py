@@ -115,7 +115,11 @@ def test_counter_prepare_on_device_matches_host_generator(wso, n):
         ws.SetWindDirection((0.3, -1.0))
         ws.PrepareCounterOnDevice(seed)
         got = ws.ExportH0()
-        ref = counter_h0(ws._raw(), seed, 0, n).reshape(n, n)
+        # wso_counter_h0 takes parameters as wso_create does (it normalises the wind direction itself): hand it the
+        # direction as given to the setter, not the stored, already normalised one
+        raw = ws._raw()
+        raw.wind_dir_x, raw.wind_dir_y = 0.3, -1.0
+        ref = counter_h0(raw, seed, 0, n).reshape(n, n)
         assert got["omega"].tobytes() == ref["omega"].tobytes()
         for f in ("re", "im"):
             # the Box-Muller draw is float64 on both sides; its rounding to fp32 and the expf may each differ by 1 ulp
