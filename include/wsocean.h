@@ -136,6 +136,30 @@ WSO_API int wso_map_host(wso_ctx* ctx, int which, const float** ptr, size_t* tex
 WSO_API int wso_map_device(wso_ctx* ctx, int which, uint32_t slot, void** dptr, size_t* texels);
 WSO_API int wso_copy_map(wso_ctx* ctx, int which, uint32_t slot, float* dst_host);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * External-memory interop: the maps land in memory a Vulkan device can bind, so the renderer's
+ * vkCmdCopyBufferToImage reads them where K2 wrote them.  Replaces: the two 16*N*N-byte memcpy calls into the mapped
+ * staging buffer and the PCIe upload behind them (WaterSurfaceMesh.cpp:701-755, vulkan/Texture2D.cpp:175-226).
+ * Both directions of VK_KHR_external_memory_fd are offered:
+ *   wso_set_exportable + wso_export_fd : the library allocates the map arrays with the CUDA virtual-memory API
+ *       (POSIX-fd shareable) and hands out a file descriptor; Vulkan imports it with VkImportMemoryFdInfoKHR
+ *       { handleType = VK_EXTERNAL_MEMORY_HANDLE_TYPE_OPAQUE_FD_BIT } and binds a VkBuffer of *bytes to it.
+ *       The caller owns the returned fd (close() it, or let the Vulkan import consume it).
+ *   wso_import_external_fd : Vulkan allocated and exported the memory (vkGetMemoryFdKHR); the library maps
+ *       [offset, offset + max_slots*16*N*N) of it as the output array of map `which`.  On success the fd belongs
+ *       to CUDA.  A tile-size change (Prepare after SetTileSize) drops the import and returns to own memory.
+ * Layout either way: [slot][N*N] RGBA32F texels, slot s at byte offset s*16*N*N (+ offset), row pitch 16*N.
+ * Map contents are reset to zero by wso_set_exportable / wso_import_external_fd; Prepare() state is kept.
+ * Ordering with the renderer: wso_import_semaphore_fd binds an exported VkSemaphore (binary: is_timeline = 0,
+ * timeline: 1; `index` 0 or 1); wso_signal_semaphore / wso_wait_semaphore enqueue a signal / wait on the context's
+ * stream after / before the work enqueued around them (value ignored for binary semaphores). */
+WSO_API int wso_set_exportable(wso_ctx* ctx, int on);
+WSO_API int wso_export_fd(wso_ctx* ctx, int which, int* fd, size_t* bytes);
+WSO_API int wso_import_external_fd(wso_ctx* ctx, int which, int fd, size_t bytes, size_t offset);
+WSO_API int wso_import_semaphore_fd(wso_ctx* ctx, int index, int fd, int is_timeline);
+WSO_API int wso_signal_semaphore(wso_ctx* ctx, int index, uint64_t value);
+WSO_API int wso_wait_semaphore(wso_ctx* ctx, int index, uint64_t value);
+
 /* Plumbing: run on a caller-owned CUDA stream (cudaStream_t as void*; NULL = the context's own), and
  * pinned host allocations for wso_compute_to_host. */
 WSO_API int wso_set_stream(wso_ctx* ctx, void* cuda_stream);

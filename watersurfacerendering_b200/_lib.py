@@ -68,6 +68,13 @@ SYMBOLS = {
     "wso_map_host": (_int, [_vp, _int, C.POINTER(_vp), C.POINTER(C.c_size_t)]),
     "wso_map_device": (_int, [_vp, _int, _u32, C.POINTER(_vp), C.POINTER(C.c_size_t)]),
     "wso_copy_map": (_int, [_vp, _int, _u32, _vp]),
+    # external-memory interop (Vulkan side of the maps)
+    "wso_set_exportable": (_int, [_vp, _int]),
+    "wso_export_fd": (_int, [_vp, _int, C.POINTER(_int), C.POINTER(C.c_size_t)]),
+    "wso_import_external_fd": (_int, [_vp, _int, _int, C.c_size_t, C.c_size_t]),
+    "wso_import_semaphore_fd": (_int, [_vp, _int, _int, _int]),
+    "wso_signal_semaphore": (_int, [_vp, _int, C.c_uint64]),
+    "wso_wait_semaphore": (_int, [_vp, _int, C.c_uint64]),
     "wso_set_stream": (_int, [_vp, _vp]),
     "wso_alloc_host": (_int, [C.c_size_t, C.POINTER(_vp)]),
     "wso_free_host": (_int, [_vp]),

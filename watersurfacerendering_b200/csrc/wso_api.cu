@@ -8,6 +8,8 @@
 #include <string>
 #include <vector>
 
+#include <cuda.h>  // types of the virtual-memory API only; entry points come from cudaGetDriverEntryPoint
+
 #include "wso_host_prepare.h"
 #include "wso_kernels.cuh"
 #include "wso_launch.h"
@@ -27,6 +29,14 @@ struct Tile {
     wso_params prepared;        // parameters the resident h0 was built with
     bool is_prepared = false;
     std::vector<wso_h0_record> h0;  // host copy in the reference layout (export / checkpoint)
+};
+
+enum BackingKind { kBackCudaMalloc = 0, kBackExportable = 1, kBackExternal = 2 };
+struct MapBacking {
+    int kind = kBackCudaMalloc;
+    CUmemGenericAllocationHandle handle = 0;  // kBackExportable
+    size_t mapped_bytes = 0;                  // kBackExportable: granularity-rounded size of the mapping
+    cudaExternalMemory_t ext = nullptr;       // kBackExternal
 };
 
 }  // namespace
@@ -57,6 +67,11 @@ struct wso_ctx {
     float4* d_norm = nullptr;
     float* d_minmax = nullptr;   // [slot][2]
     float* d_ampl = nullptr;     // [slot]
+    // how each map array (0 = displacement, 1 = normal) is backed: cudaMalloc, an exportable virtual-memory
+    // allocation, or memory imported from another API (wso_set_exportable / wso_import_external_fd)
+    MapBacking map_mem[2];
+    bool exportable = false;
+    cudaExternalSemaphore_t ext_sem[2] = {nullptr, nullptr};
     // pinned host
     float4* h_disp = nullptr;    // slot 0 mirror for wso_compute / wso_map_host
     float4* h_norm = nullptr;
@@ -113,14 +128,121 @@ bool valid_params(const wso_params& p) {
     return true;
 }
 
+// ---- CUDA virtual-memory API through the runtime's driver-entry-point lookup (libwsocean.so does not link libcuda)
+struct VmmApi {
+    CUresult (*GetGranularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
+    CUresult (*Create)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long) = nullptr;
+    CUresult (*AddressReserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+    CUresult (*Map)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+    CUresult (*SetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
+    CUresult (*Unmap)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*Release)(CUmemGenericAllocationHandle) = nullptr;
+    CUresult (*AddressFree)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*ExportHandle)(void*, CUmemGenericAllocationHandle, CUmemAllocationHandleType, unsigned long long) = nullptr;
+    bool ok = false;
+};
+
+const VmmApi& vmm_api() {
+    static const VmmApi api = [] {
+        VmmApi a;
+        bool ok = true;
+        auto get = [&](const char* name, void** fn) {
+            cudaDriverEntryPointQueryResult q;
+            if (cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess ||
+                *fn == nullptr)
+                ok = false;
+        };
+        get("cuMemGetAllocationGranularity", (void**)&a.GetGranularity);
+        get("cuMemCreate", (void**)&a.Create);
+        get("cuMemAddressReserve", (void**)&a.AddressReserve);
+        get("cuMemMap", (void**)&a.Map);
+        get("cuMemSetAccess", (void**)&a.SetAccess);
+        get("cuMemUnmap", (void**)&a.Unmap);
+        get("cuMemRelease", (void**)&a.Release);
+        get("cuMemAddressFree", (void**)&a.AddressFree);
+        get("cuMemExportToShareableHandle", (void**)&a.ExportHandle);
+        a.ok = ok;
+        return a;
+    }();
+    return api;
+}
+
+float4*& map_ptr(wso_ctx* c, int which) { return which == 0 ? c->d_disp : c->d_norm; }
+
+void free_map(wso_ctx* c, int which) {
+    MapBacking& b = c->map_mem[which];
+    float4*& p = map_ptr(c, which);
+    if (p != nullptr) {
+        if (b.kind == kBackExportable) {
+            const VmmApi& v = vmm_api();
+            v.Unmap((CUdeviceptr)p, b.mapped_bytes);
+            v.Release(b.handle);
+            v.AddressFree((CUdeviceptr)p, b.mapped_bytes);
+        } else if (b.kind == kBackExternal) {
+            cudaFree(p);  // releases the mapping of the imported object
+            cudaDestroyExternalMemory(b.ext);
+        } else {
+            cudaFree(p);
+        }
+    }
+    p = nullptr;
+    b = MapBacking{};
+}
+
+// Allocate the [slot][N*N] array of one map: cudaMalloc, or - when the context is exportable - a physical allocation
+// that can be exported as a POSIX file descriptor, mapped into a reserved address range.
+int alloc_map(wso_ctx* c, int which, size_t bytes) {
+    free_map(c, which);
+    float4*& p = map_ptr(c, which);
+    if (!c->exportable) {
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) return fail_cuda(c, e, "cudaMalloc(map)");
+        return WSO_OK;
+    }
+    const VmmApi& v = vmm_api();
+    if (!v.ok) return fail(c, WSO_ERR_CUDA, "the CUDA driver does not provide the virtual-memory API");
+    CUmemAllocationProp prop = {};
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    prop.location.id = c->device;
+    prop.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+    size_t gran = 0;
+    if (v.GetGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_MINIMUM) != CUDA_SUCCESS || gran == 0)
+        return fail(c, WSO_ERR_CUDA, "cuMemGetAllocationGranularity failed");
+    const size_t size = (bytes + gran - 1) / gran * gran;
+    MapBacking b;
+    b.kind = kBackExportable;
+    b.mapped_bytes = size;
+    CUresult r = v.Create(&b.handle, size, &prop, 0);
+    if (r != CUDA_SUCCESS)
+        return fail(c, r == CUDA_ERROR_OUT_OF_MEMORY ? WSO_ERR_OUT_OF_MEMORY : WSO_ERR_CUDA, "cuMemCreate(exportable map) failed");
+    CUdeviceptr va = 0;
+    if (v.AddressReserve(&va, size, 0, 0, 0) != CUDA_SUCCESS) {
+        v.Release(b.handle);
+        return fail(c, WSO_ERR_CUDA, "cuMemAddressReserve failed");
+    }
+    CUmemAccessDesc acc = {};
+    acc.location = prop.location;
+    acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    if (v.Map(va, size, 0, b.handle, 0) != CUDA_SUCCESS || v.SetAccess(va, size, &acc, 1) != CUDA_SUCCESS) {
+        v.Unmap(va, size);
+        v.Release(b.handle);
+        v.AddressFree(va, size);
+        return fail(c, WSO_ERR_CUDA, "cuMemMap / cuMemSetAccess failed");
+    }
+    p = reinterpret_cast<float4*>(va);
+    c->map_mem[which] = b;
+    return WSO_OK;
+}
+
 void free_device_buffers(wso_ctx* c) {
     cudaFree(c->d_h0); c->d_h0 = nullptr;
     cudaFree(c->d_hs); c->d_hs = nullptr;
     cudaFree(c->d_kv); c->d_kv = nullptr;
     cudaFree(c->d_tw); c->d_tw = nullptr;
     cudaFree(c->d_W); c->d_W = nullptr;
-    cudaFree(c->d_disp); c->d_disp = nullptr;
-    cudaFree(c->d_norm); c->d_norm = nullptr;
+    free_map(c, 0);
+    free_map(c, 1);
     cudaFree(c->d_minmax); c->d_minmax = nullptr;
     cudaFree(c->d_ampl); c->d_ampl = nullptr;
     cudaFreeHost(c->h_disp); c->h_disp = nullptr;
@@ -157,8 +279,10 @@ int allocate_for_size(wso_ctx* c, uint32_t n) {
     WSO_CUDA(c, cudaMalloc(&c->d_kv, sizeof(float) * n * c->max_tiles));
     WSO_CUDA(c, cudaMalloc(&c->d_tw, sizeof(float2) * n));
     WSO_CUDA(c, cudaMalloc(&c->d_W, w_item * chunk * 2));
-    WSO_CUDA(c, cudaMalloc(&c->d_disp, sizeof(float4) * n2 * c->max_slots));
-    WSO_CUDA(c, cudaMalloc(&c->d_norm, sizeof(float4) * n2 * c->max_slots));
+    for (int which = 0; which < 2; ++which) {
+        const int rc = alloc_map(c, which, sizeof(float4) * n2 * c->max_slots);
+        if (rc != WSO_OK) return rc;
+    }
     WSO_CUDA(c, cudaMalloc(&c->d_minmax, sizeof(float) * 2 * c->max_slots));
     WSO_CUDA(c, cudaMalloc(&c->d_ampl, sizeof(float) * c->max_slots));
     WSO_CUDA(c, cudaMallocHost(&c->h_disp, sizeof(float4) * n2));
@@ -444,6 +568,8 @@ int wso_destroy(wso_ctx* c) {
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     if (c->aux_stream) cudaStreamSynchronize(c->aux_stream);
     free_device_buffers(c);
+    for (int i = 0; i < 2; ++i)
+        if (c->ext_sem[i]) cudaDestroyExternalSemaphore(c->ext_sem[i]);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
@@ -715,6 +841,124 @@ int wso_copy_map(wso_ctx* c, int which, uint32_t slot, float* dst) {
     WSO_CUDA(c, cudaSetDevice(c->device));
     WSO_CUDA(c, cudaMemcpyAsync(dst, src, sizeof(float4) * texels, cudaMemcpyDeviceToHost, c->stream));
     WSO_CUDA(c, cudaStreamSynchronize(c->stream));
+    return WSO_OK;
+}
+
+int wso_set_exportable(wso_ctx* c, int on) {
+    if (!c) return WSO_ERR_INVALID_ARG;
+    const bool want = on != 0;
+    if (want == c->exportable && c->map_mem[0].kind != kBackExternal && c->map_mem[1].kind != kBackExternal) return WSO_OK;
+    WSO_CUDA(c, cudaSetDevice(c->device));
+    int rc = wso_sync(c);
+    if (rc != WSO_OK) return rc;
+    const bool before = c->exportable;
+    c->exportable = want;
+    const size_t bytes = sizeof(float4) * (size_t)c->n * c->n * c->max_slots;
+    for (int which = 0; which < 2; ++which) {
+        rc = alloc_map(c, which, bytes);
+        if (rc != WSO_OK) {  // fall back to what worked before; the maps must stay usable
+            c->exportable = before;
+            const std::string msg = c->err;
+            for (int w = 0; w < 2; ++w)
+                if (map_ptr(c, w) == nullptr) alloc_map(c, w, bytes);
+            return fail(c, rc, msg);
+        }
+        WSO_CUDA(c, cudaMemsetAsync(map_ptr(c, which), 0, bytes, c->stream));
+    }
+    WSO_CUDA(c, cudaStreamSynchronize(c->stream));
+    return WSO_OK;
+}
+
+int wso_export_fd(wso_ctx* c, int which, int* fd, size_t* bytes) {
+    if (!c || !fd) return WSO_ERR_INVALID_ARG;
+    if (which != WSO_MAP_DISPLACEMENT && which != WSO_MAP_NORMAL) return fail(c, WSO_ERR_INVALID_ARG, "bad map id");
+    const MapBacking& b = c->map_mem[which];
+    if (b.kind != kBackExportable)
+        return fail(c, WSO_ERR_INVALID_ARG, "map memory is not exportable: call wso_set_exportable(ctx, 1) first");
+    WSO_CUDA(c, cudaSetDevice(c->device));
+    int out = -1;
+    if (vmm_api().ExportHandle(&out, b.handle, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0) != CUDA_SUCCESS || out < 0)
+        return fail(c, WSO_ERR_CUDA, "cuMemExportToShareableHandle failed");
+    *fd = out;
+    if (bytes) *bytes = b.mapped_bytes;
+    return WSO_OK;
+}
+
+int wso_import_external_fd(wso_ctx* c, int which, int fd, size_t bytes, size_t offset) {
+    if (!c || fd < 0) return WSO_ERR_INVALID_ARG;
+    if (which != WSO_MAP_DISPLACEMENT && which != WSO_MAP_NORMAL) return fail(c, WSO_ERR_INVALID_ARG, "bad map id");
+    const size_t need = sizeof(float4) * (size_t)c->n * c->n * c->max_slots;
+    if (offset % 16 != 0 || offset > bytes || bytes - offset < need)
+        return fail(c, WSO_ERR_INVALID_ARG, "external memory too small for max_slots maps at this offset (or offset not 16-byte aligned)");
+    WSO_CUDA(c, cudaSetDevice(c->device));
+    int rc = wso_sync(c);
+    if (rc != WSO_OK) return rc;
+    cudaExternalMemoryHandleDesc hd = {};
+    hd.type = cudaExternalMemoryHandleTypeOpaqueFd;
+    hd.handle.fd = fd;
+    hd.size = bytes;
+    cudaExternalMemory_t ext = nullptr;
+    cudaError_t e = cudaImportExternalMemory(&ext, &hd);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail_cuda(c, e, "cudaImportExternalMemory");
+    }
+    cudaExternalMemoryBufferDesc bd = {};
+    bd.offset = offset;
+    bd.size = need;
+    void* ptr = nullptr;
+    e = cudaExternalMemoryGetMappedBuffer(&ptr, ext, &bd);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        cudaDestroyExternalMemory(ext);
+        return fail_cuda(c, e, "cudaExternalMemoryGetMappedBuffer");
+    }
+    free_map(c, which);
+    map_ptr(c, which) = static_cast<float4*>(ptr);
+    c->map_mem[which].kind = kBackExternal;
+    c->map_mem[which].ext = ext;
+    WSO_CUDA(c, cudaMemsetAsync(ptr, 0, need, c->stream));
+    WSO_CUDA(c, cudaStreamSynchronize(c->stream));
+    return WSO_OK;
+}
+
+int wso_import_semaphore_fd(wso_ctx* c, int index, int fd, int is_timeline) {
+    if (!c || fd < 0 || index < 0 || index > 1) return WSO_ERR_INVALID_ARG;
+    WSO_CUDA(c, cudaSetDevice(c->device));
+    cudaExternalSemaphoreHandleDesc sd = {};
+    sd.type = is_timeline ? cudaExternalSemaphoreHandleTypeTimelineSemaphoreFd : cudaExternalSemaphoreHandleTypeOpaqueFd;
+    sd.handle.fd = fd;
+    cudaExternalSemaphore_t sem = nullptr;
+    cudaError_t e = cudaImportExternalSemaphore(&sem, &sd);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail_cuda(c, e, "cudaImportExternalSemaphore");
+    }
+    if (c->ext_sem[index]) {
+        cudaStreamSynchronize(c->stream);
+        cudaDestroyExternalSemaphore(c->ext_sem[index]);
+    }
+    c->ext_sem[index] = sem;
+    return WSO_OK;
+}
+
+int wso_signal_semaphore(wso_ctx* c, int index, uint64_t value) {
+    if (!c || index < 0 || index > 1) return WSO_ERR_INVALID_ARG;
+    if (!c->ext_sem[index]) return fail(c, WSO_ERR_INVALID_ARG, "no semaphore imported at this index");
+    WSO_CUDA(c, cudaSetDevice(c->device));
+    cudaExternalSemaphoreSignalParams sp = {};
+    sp.params.fence.value = value;
+    WSO_CUDA(c, cudaSignalExternalSemaphoresAsync(&c->ext_sem[index], &sp, 1, c->stream));
+    return WSO_OK;
+}
+
+int wso_wait_semaphore(wso_ctx* c, int index, uint64_t value) {
+    if (!c || index < 0 || index > 1) return WSO_ERR_INVALID_ARG;
+    if (!c->ext_sem[index]) return fail(c, WSO_ERR_INVALID_ARG, "no semaphore imported at this index");
+    WSO_CUDA(c, cudaSetDevice(c->device));
+    cudaExternalSemaphoreWaitParams wp = {};
+    wp.params.fence.value = value;
+    WSO_CUDA(c, cudaWaitExternalSemaphoresAsync(&c->ext_sem[index], &wp, 1, c->stream));
     return WSO_OK;
 }
 

@@ -243,6 +243,30 @@ class WSTessendorf:
         L.check(self._lib.wso_map_device(self._h, which, slot, C.byref(p), C.byref(cnt)), self._h)
         return int(p.value)
 
+    # ---- external-memory interop (replaces the staging memcpy of WaterSurfaceMesh.cpp:701-755)
+    def set_exportable(self, on: bool = True):
+        """Back the map arrays with memory that can be exported as a POSIX fd (Vulkan: VK_KHR_external_memory_fd)."""
+        L.check(self._lib.wso_set_exportable(self._h, 1 if on else 0), self._h)
+
+    def export_fd(self, which: int):
+        """-> (fd, bytes) of the whole [slot][N*N] RGBA32F array of one map; the caller owns the fd."""
+        fd, nbytes = C.c_int(-1), C.c_size_t()
+        L.check(self._lib.wso_export_fd(self._h, which, C.byref(fd), C.byref(nbytes)), self._h)
+        return int(fd.value), int(nbytes.value)
+
+    def import_external_fd(self, which: int, fd: int, nbytes: int, offset: int = 0):
+        """Write one map into memory exported by another API (e.g. vkGetMemoryFdKHR); CUDA takes the fd over."""
+        L.check(self._lib.wso_import_external_fd(self._h, which, fd, nbytes, offset), self._h)
+
+    def import_semaphore_fd(self, index: int, fd: int, timeline: bool = False):
+        L.check(self._lib.wso_import_semaphore_fd(self._h, index, fd, 1 if timeline else 0), self._h)
+
+    def signal_semaphore(self, index: int, value: int = 0):
+        L.check(self._lib.wso_signal_semaphore(self._h, index, value), self._h)
+
+    def wait_semaphore(self, index: int, value: int = 0):
+        L.check(self._lib.wso_wait_semaphore(self._h, index, value), self._h)
+
     def set_stream(self, cuda_stream_ptr: Optional[int]):
         L.check(self._lib.wso_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)), self._h)
 
