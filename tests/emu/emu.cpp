@@ -78,13 +78,17 @@ static int run_cfg(const float* amp_t, const float* omega_t, const float* kv, fl
     args.items[0].slot = 0;
     args.items[0].t = t;
     {
+        // same choice as launch_tiled() in wso_kernels.cu: the lean instantiation when every item qualifies
+        using P1F = Pass1<LOGN, CP, NF, false, true>;
+        const bool fast = td.table_len > 0 && td.use_pairs != 0;
         std::vector<float2> smem(P1::SMEM_BYTES / sizeof(float2));
         std::vector<ThreadState> st(P1::T);
         for (int by = 0; by < 4 / NF; ++by)
             for (int bx = 0; bx < H / CP; ++bx) {
                 for (auto& v : smem) v = make_float2(NAN, NAN);
                 HostExec ex{P1::T, st.data()};
-                P1::run(ex, smem.data(), bx, by, 0, args);
+                if (fast) P1F::run(ex, smem.data(), bx, by, 0, args);
+                else P1::run(ex, smem.data(), bx, by, 0, args);
             }
     }
     if (w_out) std::memcpy(w_out, W.data(), W.size() * sizeof(float2));

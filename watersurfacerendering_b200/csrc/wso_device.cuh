@@ -51,11 +51,35 @@ WSO_HD void sincos_acc(float x, float* s, float* c) {
 }
 #endif
 
+// Complex arithmetic on float2.  sm_100a has packed-fp32 instructions (FADD2 / FMUL2 / FFMA2: add|mul|fma.rn.f32x2 on a
+// 64-bit register pair, each half an IEEE round-to-nearest operation) whose source operands take a half swap, a
+// per-half negation and a scalar broadcast for free.  A complex add is ONE instruction, "a + i*b" is ONE instruction,
+// a complex multiply is TWO (a.x*w + a.y*(i*w)) - half the issue slots of the scalar forms.  The transform stages are
+// add/multiply dominated and the kernels are instruction-issue bound, not FP-pipe bound.
+// The operand order inside cmul (swapped operand first) is the one ptxas folds into operand modifiers.
+#if defined(__CUDA_ARCH__) && !defined(WSO_NO_F32X2)
+WSO_HD float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+WSO_HD float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+WSO_HD float2 cadd_i(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.y, b.x)); }  // a + i*b
+WSO_HD float2 csub_i(float2 a, float2 b) { return __fadd2_rn(a, make_float2(b.y, -b.x)); }  // a - i*b
+WSO_HD float2 cadd_conj(float2 a, float2 b) { return __fadd2_rn(a, make_float2(b.x, -b.y)); }  // a + conj(b)
+WSO_HD float2 csub_conj(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, b.y)); }  // a - conj(b)
+WSO_HD float2 cscale(float s, float2 a) { return __fmul2_rn(a, make_float2(s, s)); }
+WSO_HD float2 cmul(float2 a, float2 b) {
+    return __ffma2_rn(make_float2(a.x, a.x), b, __fmul2_rn(make_float2(-b.y, b.x), make_float2(a.y, a.y)));
+}
+#else
 WSO_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 WSO_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+WSO_HD float2 cadd_i(float2 a, float2 b) { return make_float2(a.x - b.y, a.y + b.x); }
+WSO_HD float2 csub_i(float2 a, float2 b) { return make_float2(a.x + b.y, a.y - b.x); }
+WSO_HD float2 cadd_conj(float2 a, float2 b) { return make_float2(a.x + b.x, a.y - b.y); }
+WSO_HD float2 csub_conj(float2 a, float2 b) { return make_float2(a.x - b.x, a.y + b.y); }
+WSO_HD float2 cscale(float s, float2 a) { return make_float2(s * a.x, s * a.y); }
 WSO_HD float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
+#endif
 WSO_HD float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 
 // ---------------------------------------------------------------------------------------------
@@ -102,18 +126,14 @@ WSO_HD float2 mul_w16(float2 a) {
     if (e == 8) return make_float2(-a.x, -a.y);
     if (e == 12) return make_float2(a.y, -a.x);
     constexpr float h = 0.70710678118654752440f;
-    if (e == 2) return make_float2(h * (a.x - a.y), h * (a.x + a.y));
-    if (e == 6) return make_float2(h * (-a.x - a.y), h * (a.x - a.y));
-    if (e == 10) return make_float2(h * (a.y - a.x), h * (-a.x - a.y));
-    if (e == 14) return make_float2(h * (a.x + a.y), h * (a.y - a.x));
     constexpr float c1 = 0.92387953251128675613f;  // cos(pi/8)
     constexpr float s1 = 0.38268343236508977173f;  // sin(pi/8)
-    // remaining odd e: (cos, sin) of e*pi/8
-    constexpr float wc = (e == 1) ? c1 : (e == 3) ? s1 : (e == 5) ? -s1 : (e == 7) ? -c1
-                       : (e == 9) ? -c1 : (e == 11) ? -s1 : (e == 13) ? s1 : c1;
-    constexpr float ws = (e == 1) ? s1 : (e == 3) ? c1 : (e == 5) ? c1 : (e == 7) ? s1
-                       : (e == 9) ? -s1 : (e == 11) ? -c1 : (e == 13) ? -c1 : -s1;
-    return make_float2(a.x * wc - a.y * ws, a.x * ws + a.y * wc);
+    // (cos, sin) of e*pi/8
+    constexpr float wc = (e == 1) ? c1 : (e == 2) ? h : (e == 3) ? s1 : (e == 5) ? -s1 : (e == 6) ? -h : (e == 7) ? -c1
+                       : (e == 9) ? -c1 : (e == 10) ? -h : (e == 11) ? -s1 : (e == 13) ? s1 : (e == 14) ? h : c1;
+    constexpr float ws = (e == 1) ? s1 : (e == 2) ? h : (e == 3) ? c1 : (e == 5) ? c1 : (e == 6) ? h : (e == 7) ? s1
+                       : (e == 9) ? -s1 : (e == 10) ? -h : (e == 11) ? -c1 : (e == 13) ? -c1 : (e == 14) ? -h : -s1;
+    return cmul(a, make_float2(wc, ws));
 }
 
 WSO_HD void dft2(float2& a, float2& b) {
@@ -125,11 +145,10 @@ WSO_HD void dft2(float2& a, float2& b) {
 WSO_HD void dft4(float2& x0, float2& x1, float2& x2, float2& x3) {
     const float2 s0 = cadd(x0, x2), d0 = csub(x0, x2);
     const float2 s1 = cadd(x1, x3), d1 = csub(x1, x3);
-    const float2 id1 = make_float2(-d1.y, d1.x);  // i * d1
     x0 = cadd(s0, s1);
-    x1 = cadd(d0, id1);
+    x1 = cadd_i(d0, d1);
     x2 = csub(s0, s1);
-    x3 = csub(d0, id1);
+    x3 = csub_i(d0, d1);
 }
 
 template <int R>
@@ -218,20 +237,37 @@ struct DeviceExec {
         }
     }
 
-    // Fold the (min,max) every thread left in st.v[0] into out[0] (min) / out[1] (max):
-    // warp-shuffle butterfly, then one pair of atomics per warp.  Float ordering through the
-    // sign-aware int/uint trick, valid for any mix of signs.
+    // Fold the (min,max) every thread left in st.v[0] into out[0] (min) / out[1] (max): warp-shuffle butterfly,
+    // one partial per warp through shared memory, then ONE pair of atomics per CTA (all CTAs of a tile-frame hit the
+    // same two words, and same-address atomics serialise in one L2 slice).  Float ordering through the sign-aware
+    // int/uint trick, valid for any mix of signs.
     __device__ __forceinline__ void commit_minmax(float* out) {
+        __shared__ float2 partial[32];
         float mn = st.v[0].x, mx = st.v[0].y;
-        const bool full_warps = (blockDim.x & 31u) == 0u;
+        const unsigned nthreads = blockDim.x;
+        const bool full_warps = (nthreads & 31u) == 0u;
         if (full_warps) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
                 mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
             }
+            const unsigned nwarps = nthreads >> 5;
+            if (nwarps > 1) {
+                if ((threadIdx.x & 31u) == 0u) partial[threadIdx.x >> 5] = make_float2(mn, mx);
+                __syncthreads();
+                if (threadIdx.x >= 32u) return;
+                const float2 p = partial[threadIdx.x < nwarps ? threadIdx.x : 0];
+                mn = p.x;
+                mx = p.y;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+                    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                }
+            }
         }
-        if (!full_warps || (threadIdx.x & 31u) == 0u) {
+        if (!full_warps || threadIdx.x == 0u) {
             if (mn >= 0.0f) atomicMin(reinterpret_cast<int*>(out), __float_as_int(mn));
             else atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(mn));
             if (mx >= 0.0f) atomicMax(reinterpret_cast<int*>(out + 1), __float_as_int(mx));

@@ -73,12 +73,14 @@ template <> struct Cfg<13> { using Bulk = Tiling<2, 1, 1, 2>; using Lat = Bulk; 
 // 1024 resident threads per SM at <= 64 registers: every thread carries 16 complex values between barriers
 constexpr int min_blocks(int threads) { return threads >= 1024 ? 1 : (1024 / threads > 8 ? 8 : 1024 / threads); }
 
-template <int LOGN, class TL, class Args>
+// FAST = every item of the launch has the sincos table and the pair-summed records (any Prepare()-built h0): the
+// lean instantiation of K1.  FAST = false serves imported spectra that lack either property.
+template <int LOGN, class TL, class Args, bool FAST>
 __global__ void __launch_bounds__(Pass1<LOGN, TL::CP, TL::NF>::T, min_blocks(Pass1<LOGN, TL::CP, TL::NF>::T))
 wso_pass1_kernel(const __grid_constant__ Args args) {
     extern __shared__ __align__(16) float2 smem[];
     DeviceExec ex;
-    Pass1<LOGN, TL::CP, TL::NF>::run(ex, smem, blockIdx.x, blockIdx.y, blockIdx.z, args);
+    Pass1<LOGN, TL::CP, TL::NF, false, FAST>::run(ex, smem, blockIdx.x, blockIdx.y, blockIdx.z, args);
 }
 
 template <int LOGN, class TL, class Args>
@@ -127,7 +129,9 @@ static cudaError_t launch_tiled(const Args& args, int n_items, cudaStream_t stre
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 16 || !configured[dev]) {
         cudaError_t e;
-        e = cudaFuncSetAttribute(wso_pass1_kernel<LOGN, TL, Args>, cudaFuncAttributeMaxDynamicSharedMemorySize, P1::SMEM_BYTES);
+        e = cudaFuncSetAttribute(wso_pass1_kernel<LOGN, TL, Args, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P1::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(wso_pass1_kernel<LOGN, TL, Args, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P1::SMEM_BYTES);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(wso_pass2_kernel<LOGN, TL, Args>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2::SMEM_BYTES);
         if (e != cudaSuccess) return e;
@@ -138,7 +142,14 @@ static cudaError_t launch_tiled(const Args& args, int n_items, cudaStream_t stre
     cudaError_t e;
     if (ev) cudaEventRecord(ev[0], stream);
     const dim3 g1(P1::H / TL::CP, 4 / TL::NF, n_items);
-    e = launch_pdl(wso_pass1_kernel<LOGN, TL, Args>, g1, P1::T, P1::SMEM_BYTES, stream, args);
+#ifdef WSO_EXP_NO_FAST
+    bool fast = false;
+#else
+    bool fast = true;
+#endif
+    for (int i = 0; i < n_items; ++i) fast = fast && args.td[i].table_len > 0 && args.td[i].use_pairs != 0;
+    e = fast ? launch_pdl(wso_pass1_kernel<LOGN, TL, Args, true>, g1, P1::T, P1::SMEM_BYTES, stream, args)
+             : launch_pdl(wso_pass1_kernel<LOGN, TL, Args, false>, g1, P1::T, P1::SMEM_BYTES, stream, args);
     if (e != cudaSuccess) return e;
     if (ev) cudaEventRecord(ev[1], stream);
     const dim3 gh(PH::H / TL::RH, 1, n_items);

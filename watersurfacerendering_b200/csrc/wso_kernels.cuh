@@ -176,7 +176,10 @@ WSO_HD void pack_interior(float s0, float kx0, float kz0, float inv0, float s1, 
 // -------------------------------------------------------------------------------------------------
 // K1
 // -------------------------------------------------------------------------------------------------
-template <int LOGN, int CP, int NF, bool SLAB = false>
+// FAST: the launch guarantees table_len > 0 and use_pairs for every item (any h0 built by Prepare()): the direct
+// sincosf and per-point-record variants of the evolve loop are not instantiated - the kernel's code shrinks from
+// ~170 KB to what the hot path needs (instruction-cache misses showed up as 7 % of K1's stall cycles).
+template <int LOGN, int CP, int NF, bool SLAB = false, bool FAST = false>
 struct Pass1 {
     static constexpr int N = 1 << LOGN;
     static constexpr int H = N / 2;
@@ -266,11 +269,40 @@ struct Pass1 {
     // Interior items read the pair-summed records; all records of a row pair are requested before any is
     // used, so the L2 latency is paid once per row pair instead of once per item.
     static constexpr int CPT = CP / CG;  // column pairs per thread
+    // The records of a thread's FIRST row pair are requested at the very top of the kernel (prefetch_thread) and
+    // parked in the 16 complex registers that the transform stages use later: the L2 round trip overlaps the
+    // sincos-table build, its barrier and the special row pair below.
+#ifdef WSO_EXP_NO_PREFETCH
+    static constexpr bool kPrefetch = false;
+#else
+    static constexpr bool kPrefetch = (2 * CPT * (int)sizeof(float4) <= kValsPerThread * (int)sizeof(float2));
+#endif
+
+    static WSO_HD const float4* pair_record(const TileDev& td, int bx, int cg, int k, int i) {
+        const int jl = bx * CP + cg + k * CG;
+        return td.hs + ((size_t)jl * H + i) * 2;
+    }
+
+    static WSO_HD void prefetch_thread(const TileDev& td, int bx, int tid, ThreadState& st) {
+        if (!kPrefetch || (!FAST && !td.use_pairs)) return;
+        const int i0 = tid % IT, cg = tid / IT;
+        if (i0 == 0) return;
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) {
+            const float4* rec = pair_record(td, bx, cg, k, i0);
+            const float4 a = rec[0], b = rec[1];
+            st.v[4 * k + 0] = make_float2(a.x, a.y);
+            st.v[4 * k + 1] = make_float2(a.z, a.w);
+            st.v[4 * k + 2] = make_float2(b.x, b.y);
+            st.v[4 * k + 3] = make_float2(b.z, b.w);
+        }
+    }
+
     template <bool TABLE>
     static WSO_HD void evolve_thread(const TileDev& td, const float2* table, float t, int fg, float2* smem, int bx,
-                                     int tid) {
+                                     int tid, const ThreadState& st) {
         const int i0 = tid % IT, cg = tid / IT;
-        if (!td.use_pairs) {  // foreign h0 (omega(k) != omega(-k)): every item through the per-point records
+        if (!FAST && !td.use_pairs) {  // foreign h0 (omega(k) != omega(-k)): every item through the per-point records
             for (int i = i0; i < H; i += IT)
                 for (int cp = cg; cp < CP; cp += CG) evolve_item_general<TABLE>(td, table, t, fg, smem, cp, i, bx * CP + cp);
             return;
@@ -286,12 +318,19 @@ struct Pass1 {
         for (int i = i0; i < H; i += IT) {
             if (i == 0) continue;
             float4 q0[CPT], q1[CPT];
+            if (kPrefetch && i == i0) {
 #pragma unroll
-            for (int k = 0; k < CPT; ++k) {
-                const int jl = bx * CP + cg + k * CG;
-                const float4* rec = td.hs + ((size_t)jl * H + i) * 2;
-                q0[k] = rec[0];
-                q1[k] = rec[1];
+                for (int k = 0; k < CPT; ++k) {
+                    q0[k] = make_float4(st.v[4 * k + 0].x, st.v[4 * k + 0].y, st.v[4 * k + 1].x, st.v[4 * k + 1].y);
+                    q1[k] = make_float4(st.v[4 * k + 2].x, st.v[4 * k + 2].y, st.v[4 * k + 3].x, st.v[4 * k + 3].y);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < CPT; ++k) {
+                    const float4* rec = pair_record(td, bx, cg, k, i);
+                    q0[k] = rec[0];
+                    q1[k] = rec[1];
+                }
             }
             const float kzA = td.kv[i];
             const int eA = pad_idx(i), eB = pad_idx(N - i);
@@ -317,9 +356,12 @@ struct Pass1 {
         const TileDev& td = args.td[bz];
         const float t = item.t;
 
+        // ---- request the first row pair's records before anything else ---------------------------------
+        ex.each([&](int tid, ThreadState& st) { prefetch_thread(td, bx, tid, st); });
+
         // ---- per-frame (cos,sin)(omega_j * t) table: omega takes few distinct values j*omega0 ------
         float2* table = smem + B * LS;
-        const bool use_table = td.table_len > 0;
+        const bool use_table = FAST || td.table_len > 0;
         if (use_table) {
             ex.each([&](int tid, ThreadState&) {
                 for (int j = tid; j < td.table_len; j += T) {
@@ -333,9 +375,9 @@ struct Pass1 {
 
         // ---- evolve: 4 wave vectors per work item, all NF fields ------------------------------------
 #ifndef WSO_EXP_SKIP_EVOLVE
-        ex.each([&](int tid, ThreadState&) {
-            if (use_table) evolve_thread<true>(td, table, t, by, smem, bx, tid);
-            else evolve_thread<false>(td, table, t, by, smem, bx, tid);
+        ex.each([&](int tid, ThreadState& st) {
+            if (FAST || use_table) evolve_thread<true>(td, table, t, by, smem, bx, tid, st);
+            else if constexpr (!FAST) evolve_thread<false>(td, table, t, by, smem, bx, tid, st);
         });
 #endif
         ex.sync();
@@ -375,8 +417,10 @@ struct Pass1 {
                 const float2* line = smem + (fl * CP + cp) * LS;
                 const float2 c1 = line[pad_idx(mp)];
                 const float2 c2 = line[pad_idx((N - mp) & (N - 1))];
-                float2 wa = make_float2(0.5f * (c1.x + c2.x), 0.5f * (c1.y - c2.y));
-                float2 wb = make_float2(0.5f * (c1.y + c2.y), -0.5f * (c1.x - c2.x));
+                // column n=j: (c1 + conj(c2))/2, column n=N-j: -i*(c1 - conj(c2))/2
+                float2 wa = cscale(0.5f, cadd_conj(c1, c2));
+                const float2 d = csub_conj(c1, c2);
+                float2 wb = cscale(0.5f, make_float2(d.y, -d.x));
                 if (mp == 0) {  // pack the (real) Nyquist bin m'=N/2 into the imaginary part of m'=0
                     const float2 ch = line[pad_idx(H)];
                     wa.y = ch.x;
