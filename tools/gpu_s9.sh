@@ -1,0 +1,19 @@
+#!/bin/bash
+# Dev tool (under gpurun, one GPU): parity tests on the in-tree build, bench c1-c4, then every variant library in
+# build/variants/ (name n<LOGN>_*) on the workload of its size.   usage: bash tools/gpu_s9.sh TAG
+TAG=${1:-r1i}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/smi.txt 2>&1
+timeout 420 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_gpu.log
+for wl in c2 c3 c4 c1; do
+  timeout 200 python bench.py --workload $wl --no-cpu-baseline > $OUT/bench_$wl.json 2> $OUT/bench_$wl.err; echo "bench $wl rc=$?"
+done
+for n in 512 1024; do timeout 60 tools/lat_bench $n 2000 >> $OUT/lat_bench.jsonl 2>> $OUT/lat_bench.err; done
+for so in build/variants/libwsocean_n*.so; do
+  [ -f $so ] || continue
+  name=$(basename $so .so); name=${name#libwsocean_}
+  case $name in n9_*) wl=c4;; n10_*) wl=c2;; n11_*) wl=c3;; *) wl=c2;; esac
+  WSO_LIB_PATH=$PWD/$so timeout 100 python bench.py --workload $wl --steps 5 --warmup 3 --no-cpu-baseline > $OUT/var_${name}.json 2> $OUT/var_${name}.err
+done
+tail -n 3 $OUT/pytest_gpu.log; cat $OUT/lat_bench.jsonl; python tools/summ.py $OUT/bench_c?.json $OUT/var_*.json

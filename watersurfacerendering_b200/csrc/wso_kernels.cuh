@@ -272,10 +272,17 @@ struct Pass1 {
     // The records of a thread's FIRST row pair are requested at the very top of the kernel (prefetch_thread) and
     // parked in the 16 complex registers that the transform stages use later: the L2 round trip overlaps the
     // sincos-table build, its barrier and the special row pair below.
+    // Measured on B200 (profiles/r1h_ab_variants.txt): neutral at 1024^2 (one row pair per thread), but at 2048^2,
+    // where a thread walks two row pairs, parking the first pair's records costs more than it hides (K1 68.3 ->
+    // 56.3 us per tile-frame without it): only grids whose threads own a single row pair prefetch.
+#ifndef WSO_TUNE_PREFETCH_MAX_LOGN
+#define WSO_TUNE_PREFETCH_MAX_LOGN 10
+#endif
 #ifdef WSO_EXP_NO_PREFETCH
     static constexpr bool kPrefetch = false;
 #else
-    static constexpr bool kPrefetch = (2 * CPT * (int)sizeof(float4) <= kValsPerThread * (int)sizeof(float2));
+    static constexpr bool kPrefetch = (LOGN <= WSO_TUNE_PREFETCH_MAX_LOGN) &&
+                                      (2 * CPT * (int)sizeof(float4) <= kValsPerThread * (int)sizeof(float2));
 #endif
 
     static WSO_HD const float4* pair_record(const TileDev& td, int bx, int cg, int k, int i) {
@@ -407,13 +414,22 @@ struct Pass1 {
         // ---- split the two real columns, keep m' in [0, N/2), store W[m'][f][slot] ---------------
         // thread -> fixed column pair cp = tid % CP (CP adjacent slots = one 8*CP-byte segment per m'),
         // and (field, m') pairs rest = tid/CP + k*(T/CP)
+        // The sweep structure is compile-time: SWEEPS = 8 fully unrolled iterations (all shared-memory loads of a thread
+        // are in flight together; a rolled loop paid one LDS round trip and ~20 index instructions per iteration -
+        // 22 % of K1's executed instructions in profiles/r1h_ncu_c2.txt).
         float2* Wit = args.W + (size_t)bz * ((size_t)H * 4 * N);
+        constexpr int STEP = T / CP;             // (field, m') pairs covered per sweep of the CTA
+        constexpr int SWEEPS = NF * H / STEP;    // = 8
+        constexpr int PER_LINE = H / STEP;       // sweeps per packed field
+        static_assert(STEP >= 1 && H % STEP == 0 && SWEEPS * STEP == NF * H, "bad split tiling");
         ex.each([&](int tid, ThreadState&) {
             const int cp = tid % CP;
             const int jl = bx * CP + cp;
-            for (int rest = tid / CP; rest < NF * H; rest += T / CP) {
-                const int mp = rest % H;
-                const int fl = rest / H;
+            const int b = tid / CP;              // m' of the first sweep, < STEP
+#pragma unroll
+            for (int k = 0; k < SWEEPS; ++k) {
+                const int fl = k / PER_LINE;
+                const int mp = b + (k % PER_LINE) * STEP;
                 const float2* line = smem + (fl * CP + cp) * LS;
                 const float2 c1 = line[pad_idx(mp)];
                 const float2 c2 = line[pad_idx((N - mp) & (N - 1))];
@@ -421,10 +437,12 @@ struct Pass1 {
                 float2 wa = cscale(0.5f, cadd_conj(c1, c2));
                 const float2 d = csub_conj(c1, c2);
                 float2 wb = cscale(0.5f, make_float2(d.y, -d.x));
-                if (mp == 0) {  // pack the (real) Nyquist bin m'=N/2 into the imaginary part of m'=0
-                    const float2 ch = line[pad_idx(H)];
-                    wa.y = ch.x;
-                    wb.y = ch.y;
+                if (k % PER_LINE == 0) {
+                    if (mp == 0) {  // pack the (real) Nyquist bin m'=N/2 into the imaginary part of m'=0
+                        const float2 ch = line[pad_idx(H)];
+                        wa.y = ch.x;
+                        wb.y = ch.y;
+                    }
                 }
                 const int f = by * NF + fl;
                 if constexpr (SLAB) {
@@ -542,7 +560,9 @@ struct Pass2 {
             // (-1)^(row+col): loop invariant when the column stride GI is even (N >= 32)
             float s = ((mp + lt) & 1) ? -1.0f : 1.0f;
             if (mp != 0) {
-                for (int c = lt; c < N; c += GI) {
+#pragma unroll
+                for (int k = 0; k < N / GI; ++k) {  // compile-time trip count: the loads of a thread overlap
+                    const int c = lt + k * GI;
                     if (GI & 1) s = ((mp + c) & 1) ? -1.0f : 1.0f;
                     const float h = rmul(l0[pad_idx(c)].x, s);
                     mn = h < mn ? h : mn;
@@ -565,22 +585,37 @@ struct Pass2 {
     // ---- K2 pack: each transformed line pair (l0, l1) yields output rows A = m' and B = N-m' (rows 0 and N/2 for
     // m' = 0).  rows: bit 0 = write row A, bit 1 = write row B.
     // reference: WSTessendorf.cpp:385-437 (sign, lambda, packing) and :443-455 (normalisation)
+    // STRIDE (threads per row item) is a compile-time constant: the N/STRIDE = 8 column visits of a thread are fully
+    // unrolled, so all of its shared-memory loads are in flight together (a rolled loop paid one LDS round trip per
+    // visit: 23 % of K2's executed instructions and its top stall line in profiles/r1h_ncu_c2.txt).
+    template <int STRIDE>
     static WSO_HD void pack_item(const float2* l0, const float2* l1, int mp, float4* outA, float4* outB, int by,
-                                 float lambda, float inv_amp, int lt, int stride, int rows) {
+                                 float lambda, float inv_amp, int lt, int rows) {
+        static_assert(N % STRIDE == 0, "bad pack stride");
+        constexpr int VISITS = N / STRIDE;
         // (-1)^(row+col) is the same for both output rows and every column this thread visits (stride is even)
         const float s = ((mp + lt) & 1) ? -1.0f : 1.0f;
         const float sl = rmul(s, lambda);
         if (mp != 0) {
-            for (int c = lt; c < N; c += stride) {
-                const int e = pad_idx(c);
-                const float2 a0 = l0[e], a1 = l1[e];
-                const int cm = (N - c) & (N - 1);   // row N-m' is the conjugate mirror of row m'
-                if (by == 0) {
+            if (by == 0) {
+#pragma unroll
+                for (int k = 0; k < VISITS; ++k) {
+                    const int c = lt + k * STRIDE;
+                    const int e = pad_idx(c);
+                    const float2 a0 = l0[e], a1 = l1[e];
+                    const int cm = (N - c) & (N - 1);   // row N-m' is the conjugate mirror of row m'
                     const float y = rmul(rmul(a0.x, s), inv_amp);
                     const float x = rmul(sl, a0.y), z = rmul(sl, a1.y);
                     if (rows & 1) outA[c] = make_float4(x, y, z, 1.0f);
                     if (rows & 2) outB[cm] = make_float4(-x, y, -z, 1.0f);
-                } else {
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < VISITS; ++k) {
+                    const int c = lt + k * STRIDE;
+                    const int e = pad_idx(c);
+                    const float2 a0 = l0[e], a1 = l1[e];
+                    const int cm = (N - c) & (N - 1);
                     const float4 ta = make_float4(s * a0.y, s * a1.y, s * a0.x, s * a1.x);
                     if (rows & 1) outA[c] = ta;
                     if (rows & 2) outB[cm] = make_float4(-ta.x, -ta.y, ta.z, ta.w);
@@ -588,7 +623,7 @@ struct Pass2 {
             }
         } else {
             // rows 0 and N/2 were transformed as one complex line: separate them
-            for (int c = lt; c < N; c += stride) {
+            for (int c = lt; c < N; c += STRIDE) {
                 const int e = pad_idx(c), em = pad_idx((N - c) & (N - 1));
                 const float2 p0 = l0[e], p1 = l1[e], m0 = l0[em], m1 = l1[em];
                 const float2 a0 = make_float2(0.5f * (p0.x + m0.x), 0.5f * (p0.y - m0.y));
@@ -640,7 +675,7 @@ struct Pass2 {
             }
             float4* outA = out + (size_t)(SLAB ? ml : mp) * N;
             float4* outB = out + (size_t)(SLAB ? (1 << hlog) + ml : (mp == 0 ? H : N - mp)) * N;
-            pack_item(l0, l1, mp, outA, outB, by, lambda, inv_amp, lt, GI, rows);
+            pack_item<GI>(l0, l1, mp, outA, outB, by, lambda, inv_amp, lt, rows);
         });
     }
 
