@@ -16,4 +16,11 @@ for so in build/variants/libwsocean_n*.so; do
   case $name in n9_*) wl=c4;; n10_*) wl=c2;; n11_*) wl=c3;; *) wl=c2;; esac
   WSO_LIB_PATH=$PWD/$so timeout 100 python bench.py --workload $wl --steps 5 --warmup 3 --no-cpu-baseline > $OUT/var_${name}.json 2> $OUT/var_${name}.err
 done
+# W scratch budget per chunk (WSO_W_BUDGET_MB, default 48): tile-frames per launch triple
+if [ "$2" = budget ]; then
+  for cfg in c2:16 c2:32 c2:64 c2:96 c3:128 c3:192 c4:24 c4:96; do
+    wl=${cfg%%:*}; mb=${cfg##*:}
+    WSO_W_BUDGET_MB=$mb timeout 100 python bench.py --workload $wl --steps 5 --warmup 3 --no-cpu-baseline > $OUT/var_budget_${wl}_${mb}mb.json 2> $OUT/var_budget_${wl}_${mb}mb.err
+  done
+fi
 tail -n 3 $OUT/pytest_gpu.log; cat $OUT/lat_bench.jsonl; python tools/summ.py $OUT/bench_c?.json $OUT/var_*.json

@@ -35,11 +35,11 @@ template <> struct Cfg<8>  { using Bulk = Tiling<4, 4, 4, 8>;   using Lat = Tili
 #define WSO_TUNE_CP10 4
 #define WSO_TUNE_NF10 2
 #define WSO_TUNE_RI10 2
-#define WSO_TUNE_RH10 8
+#define WSO_TUNE_RH10 4
 #endif
 #ifndef WSO_TUNE_CP11
 #define WSO_TUNE_CP11 4
-#define WSO_TUNE_NF11 1
+#define WSO_TUNE_NF11 2
 #define WSO_TUNE_RI11 1
 #define WSO_TUNE_RH11 2
 #endif
@@ -80,6 +80,14 @@ __global__ void __launch_bounds__(Pass1<LOGN, TL::CP, TL::NF>::T, min_blocks(Pas
 wso_pass1_kernel(const __grid_constant__ Args args) {
     extern __shared__ __align__(16) float2 smem[];
     DeviceExec ex;
+#ifdef WSO_EXP_STAGGER_K1_NS
+    // experiment: the CTAs that fill the second resident slot of every SM in the first wave start late, so that the two
+    // co-resident CTAs are in different phases (evolve = L2 latency, transform = shared memory, split = stores)
+    {
+        const unsigned lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+        if (lin >= 148u && lin < 296u) __nanosleep(WSO_EXP_STAGGER_K1_NS);
+    }
+#endif
     Pass1<LOGN, TL::CP, TL::NF, false, FAST>::run(ex, smem, blockIdx.x, blockIdx.y, blockIdx.z, args);
 }
 

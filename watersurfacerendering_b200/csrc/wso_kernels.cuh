@@ -585,9 +585,13 @@ struct Pass2 {
     // ---- K2 pack: each transformed line pair (l0, l1) yields output rows A = m' and B = N-m' (rows 0 and N/2 for
     // m' = 0).  rows: bit 0 = write row A, bit 1 = write row B.
     // reference: WSTessendorf.cpp:385-437 (sign, lambda, packing) and :443-455 (normalisation)
-    // STRIDE (threads per row item) is a compile-time constant: the N/STRIDE = 8 column visits of a thread are fully
-    // unrolled, so all of its shared-memory loads are in flight together (a rolled loop paid one LDS round trip per
-    // visit: 23 % of K2's executed instructions and its top stall line in profiles/r1h_ncu_c2.txt).
+    // STRIDE: threads per row item.  The column loop stays rolled: fully unrolled (all 16 shared-memory loads of a
+    // thread in flight) it measured 6-8 % SLOWER on B200 (K2 9.35 -> 10.1 us per 1024^2 tile-frame, profiles/
+    // r1i_sweep.txt) - the map stores of K2 are what bounds it, and they issue best interleaved with the loads.
+#ifndef WSO_TUNE_PACK_UNROLL
+#define WSO_TUNE_PACK_UNROLL 1
+#endif
+    static constexpr int kPackUnroll = WSO_TUNE_PACK_UNROLL;
     template <int STRIDE>
     static WSO_HD void pack_item(const float2* l0, const float2* l1, int mp, float4* outA, float4* outB, int by,
                                  float lambda, float inv_amp, int lt, int rows) {
@@ -598,7 +602,7 @@ struct Pass2 {
         const float sl = rmul(s, lambda);
         if (mp != 0) {
             if (by == 0) {
-#pragma unroll
+#pragma unroll kPackUnroll
                 for (int k = 0; k < VISITS; ++k) {
                     const int c = lt + k * STRIDE;
                     const int e = pad_idx(c);
@@ -610,7 +614,7 @@ struct Pass2 {
                     if (rows & 2) outB[cm] = make_float4(-x, y, -z, 1.0f);
                 }
             } else {
-#pragma unroll
+#pragma unroll kPackUnroll
                 for (int k = 0; k < VISITS; ++k) {
                     const int c = lt + k * STRIDE;
                     const int e = pad_idx(c);
