@@ -50,7 +50,9 @@ def test_emulated_intermediate_layout_matches_model():
         assert rel_l2(w[:, f, :], Wm[:, f, :]) < 2e-6, f"field {f}"
 
 
-@pytest.mark.parametrize("n,variant", [(512, 1), (1024, 0)])
+# (512, 0), (1024, 0), (2048, 0): tilings with NF * R0 == 8 - K1 runs its fused front end (evolve + first stage in
+# registers); (512, 1): the unfused path
+@pytest.mark.parametrize("n,variant", [(512, 0), (512, 1), (1024, 0), (2048, 0)])
 def test_emulated_kernels_vs_oracle_large(n, variant):
     rng = np.random.default_rng(n)
     xi = (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))).astype(np.complex64)

@@ -261,10 +261,11 @@ int allocate_for_size(wso_ctx* c, uint32_t n) {
     c->logn = logn;
     c->first_use = true;
     const size_t n2 = (size_t)n * n;
-    // chunk: tile-frames per launch.  Keep the W scratch of one chunk around 48 MB so it stays in the
-    // 126 MB L2 between K1 and K2.
+    // chunk: tile-frames per launch.  Keep the W scratch of one chunk around 64 MB so it stays in the
+    // 126 MB L2 between K1 and K2 (16/32/48/64/96 MB measured on B200, profiles/r1j_sweep.txt:
+    // 1024^2 42.5k / 52.8k / 52.6k / 54.9k / 54.8k tile-frames/s).
     const size_t w_item = n2 * 16;
-    size_t budget_mb = 48;
+    size_t budget_mb = 64;
     if (const char* env = std::getenv("WSO_W_BUDGET_MB")) {
         const long v = std::atol(env);
         if (v > 0 && v <= 65536) budget_mb = (size_t)v;

@@ -90,6 +90,19 @@ struct Point {
     float H, kx, kz, ux, uz;
 };
 
+// compile-time loop: f(std::integral_constant<int, I>) for I = 0..N-1 (register arrays need constant indices)
+template <int I>
+struct IntC {
+    static constexpr int value = I;
+};
+template <int I, int N, class F>
+WSO_HD void static_for(F&& f) {
+    if constexpr (I < N) {
+        f(IntC<I>{});
+        static_for<I + 1, N>(f);
+    }
+}
+
 // h~(k,t) for the wave vector whose 16-byte record is q.
 // reference: WaveHeightFT, WSTessendorf.h:265-275 with heightAmp_conj == conj(heightAmp) (validated at
 // import): h~ = 2*(a*cos(wt) - b*sin(wt)), imaginary part exactly 0.
@@ -356,6 +369,197 @@ struct Pass1 {
         }
     }
 
+    // ---------------------------------------------------------------------------------------------------------
+    // Fused front end (FAST launches whose tiling has NF * R0 == 8): evolve + FIRST Stockham stage in registers.
+    // The first stage's butterfly j of a line reads rows j + r*JN0 (r < R0); the Hermitian mirror of those rows is
+    // butterfly JN0 - j read backwards.  A thread that owns the butterfly pair (u, JN0-u) of the NF lines of one
+    // column pair therefore needs exactly R0 row pairs (a, N-a) - the unit the pair-summed records are stored in -
+    // and ends up with 2 * R0 * NF = 16 complex values: it runs the radix-R0 butterflies on them and writes the
+    // stage-0 OUTPUT.  Against "evolve -> shared memory -> stage-0 load" this saves 16 STS.64 + 16 LDS.64 per thread
+    // and one barrier (K1's transform phase runs at ~2/3 of the shared-memory wavefront bound).
+    //   thread u >= 1: butterflies X = u, Y = JN0 - u.   thread u == 0: the two self-mirrored butterflies X = 0
+    //   (rows r*JN0, holds the special rows 0 and N/2) and Y = JN0/2.
+    // v[(fl*2 + bf)*R0 + idx]: line slot fl, bf 0 = X / 1 = Y, idx = input index r of that butterfly.
+    static constexpr int R0 = Plan<LOGN>::R[0];
+    static constexpr int JN0 = N / R0;
+    static constexpr int H2 = JN0 / 2;  // threads per column pair
+#ifdef WSO_EXP_NO_FUSE0
+    static constexpr bool kFuse0 = false;
+#else
+    static constexpr bool kFuse0 = FAST && Plan<LOGN>::S > 1 && NF * R0 == 8 && H2 >= 2 && T == CP * H2;
+#endif
+    static constexpr bool kPrefetchF = kFuse0 && 4 * R0 <= kValsPerThread;  // all 2*R0 records fit the parking space
+
+    // packed field in line slot FL of field group fg: F = fg*NF + FL (fg is CTA-uniform)
+    template <int FL>
+    static WSO_HD void interior_fl(int fg, float s0, float kx0, float kz0, float inv0, float s1, float kx1, float kz1,
+                                   float inv1, float2* a, float2* b) {
+        if constexpr (NF == 4) {
+            pack_interior<FL>(s0, kx0, kz0, inv0, s1, kx1, kz1, inv1, a, b);
+        } else if constexpr (NF == 2) {
+            if (fg == 0) pack_interior<FL>(s0, kx0, kz0, inv0, s1, kx1, kz1, inv1, a, b);
+            else pack_interior<FL + 2>(s0, kx0, kz0, inv0, s1, kx1, kz1, inv1, a, b);
+        } else {
+            if (fg == 0) pack_interior<0>(s0, kx0, kz0, inv0, s1, kx1, kz1, inv1, a, b);
+            else if (fg == 1) pack_interior<1>(s0, kx0, kz0, inv0, s1, kx1, kz1, inv1, a, b);
+            else if (fg == 2) pack_interior<2>(s0, kx0, kz0, inv0, s1, kx1, kz1, inv1, a, b);
+            else pack_interior<3>(s0, kx0, kz0, inv0, s1, kx1, kz1, inv1, a, b);
+        }
+    }
+    template <int FL>
+    static WSO_HD void general_fl(int fg, const Point (&pt)[4], int mask, float2* a, float2* b) {
+        if constexpr (NF == 4) {
+            pack_general<FL>(pt, mask, a, b);
+        } else if constexpr (NF == 2) {
+            if (fg == 0) pack_general<FL>(pt, mask, a, b);
+            else pack_general<FL + 2>(pt, mask, a, b);
+        } else {
+            if (fg == 0) pack_general<0>(pt, mask, a, b);
+            else if (fg == 1) pack_general<1>(pt, mask, a, b);
+            else if (fg == 2) pack_general<2>(pt, mask, a, b);
+            else pack_general<3>(pt, mask, a, b);
+        }
+    }
+
+    // the four wave vectors of work item (row pair i, column pair jl) from the per-point records (same loads and
+    // products as evolve_item_general)
+    template <bool TABLE>
+    static WSO_HD int general_points(const TileDev& td, const float2* table, float t, int i, int jl, Point (&pt)[4]) {
+        const int j = td.j0 + jl;
+        const int mA = i, mB = (i == 0) ? H : N - i;
+        const int nA = j, nB = (j == 0) ? H : N - j;
+        const float kxA = td.kv[nA], kxB = td.kv[nB], kzA = td.kv[mA], kzB = td.kv[mB];
+        const float4* colA = td.h0 + (size_t)jl * 2 * N;
+        const float4* colB = colA + N;
+        const float4 q0 = colA[mA], q1 = colB[mA];
+        const float4 q2 = colA[mB], q3 = colB[mB];
+        const float h0 = eval_height<TABLE>(q0, table, t), h1 = eval_height<TABLE>(q1, table, t);
+        const float h2 = eval_height<TABLE>(q2, table, t), h3 = eval_height<TABLE>(q3, table, t);
+        pt[0] = Point{h0, kxA, kzA, rmul(kxA, q0.z), rmul(kzA, q0.z)};
+        pt[1] = Point{h1, kxB, kzA, rmul(kxB, q1.z), rmul(kzA, q1.z)};
+        pt[2] = Point{h2, kxA, kzB, rmul(kxA, q2.z), rmul(kzB, q2.z)};
+        pt[3] = Point{h3, kxB, kzB, rmul(kxB, q3.z), rmul(kzB, q3.z)};
+        return ((i != 0) ? 2 : 0) | ((j != 0) ? 1 : 0);
+    }
+
+    // register slot of the row-A / row-B output of work item K in the GENERIC arrangement (u >= 1):
+    //   K <  R0/2 : a = u + K*JN0          A -> X[K]         B -> Y[R0-1-K]
+    //   K >= R0/2 : a = JN0-u + (K-R0/2)*JN0  A -> Y[K-R0/2]   B -> X[R0-1-(K-R0/2)]
+    template <int FL, int K>
+    static constexpr int slot_a() { return K < R0 / 2 ? (FL * 2 + 0) * R0 + K : (FL * 2 + 1) * R0 + (K - R0 / 2); }
+    template <int FL, int K>
+    static constexpr int slot_b() {
+        return K < R0 / 2 ? (FL * 2 + 1) * R0 + (R0 - 1 - K) : (FL * 2 + 0) * R0 + (R0 - 1 - (K - R0 / 2));
+    }
+
+    static WSO_HD void prefetch_fused(const TileDev& td, int bx, int tid, ThreadState& st) {
+        if (!kPrefetchF) return;
+        const int cp = tid / H2, u = tid - cp * H2;
+        const int jl = bx * CP + cp;
+        const int base2 = u ? JN0 - u : JN0 / 2;
+        static_for<0, R0>([&](auto kc) {
+            constexpr int K = decltype(kc)::value;
+            const int a = K < R0 / 2 ? u + K * JN0 : base2 + (K - R0 / 2) * JN0;
+            const float4* rec = td.hs + ((size_t)jl * H + a) * 2;
+            const float4 q0 = rec[0], q1 = rec[1];
+            st.v[4 * K + 0] = make_float2(q0.x, q0.y);
+            st.v[4 * K + 1] = make_float2(q0.z, q0.w);
+            st.v[4 * K + 2] = make_float2(q1.x, q1.y);
+            st.v[4 * K + 3] = make_float2(q1.z, q1.w);
+        });
+    }
+
+    static WSO_HD void fused_thread(const TileDev& td, const float2* table, float t, int fg, float2* smem, int bx,
+                                    int tid, ThreadState& st) {
+        const int cp = tid / H2, u = tid - cp * H2;
+        const int jl = bx * CP + cp, j = td.j0 + jl;
+        const int base2 = u ? JN0 - u : JN0 / 2;
+        float2 out[kValsPerThread];
+        if (j != 0) {
+            float4 q0[R0], q1[R0];
+            static_for<0, R0>([&](auto kc) {
+                constexpr int K = decltype(kc)::value;
+                if (kPrefetchF) {
+                    q0[K] = make_float4(st.v[4 * K + 0].x, st.v[4 * K + 0].y, st.v[4 * K + 1].x, st.v[4 * K + 1].y);
+                    q1[K] = make_float4(st.v[4 * K + 2].x, st.v[4 * K + 2].y, st.v[4 * K + 3].x, st.v[4 * K + 3].y);
+                } else {
+                    const int a = K < R0 / 2 ? u + K * JN0 : base2 + (K - R0 / 2) * JN0;
+                    const float4* rec = td.hs + ((size_t)jl * H + a) * 2;
+                    q0[K] = rec[0];
+                    q1[K] = rec[1];
+                }
+            });
+            const float kxA = td.kv[j], kxB = td.kv[N - j];
+            static_for<0, R0>([&](auto kc) {
+                constexpr int K = decltype(kc)::value;
+                const int a = K < R0 / 2 ? u + K * JN0 : base2 + (K - R0 / 2) * JN0;
+                const float kz = td.kv[a];
+                const float s0 = 0.5f * eval_height<true>(q0[K], table, t);
+                const float s1 = 0.5f * eval_height<true>(q1[K], table, t);
+                static_for<0, NF>([&](auto fc) {
+                    constexpr int FL = decltype(fc)::value;
+                    interior_fl<FL>(fg, s0, kxA, kz, q0[K].z, s1, kxB, kz, q1[K].z, &out[slot_a<FL, K>()],
+                                    &out[slot_b<FL, K>()]);
+                });
+            });
+        } else {  // column pair (0, N/2): every item through the per-point records
+            static_for<0, R0>([&](auto kc) {
+                constexpr int K = decltype(kc)::value;
+                const int a = K < R0 / 2 ? u + K * JN0 : base2 + (K - R0 / 2) * JN0;
+                Point pt[4];
+                const int mask = general_points<true>(td, table, t, a, jl, pt);
+                static_for<0, NF>([&](auto fc) {
+                    constexpr int FL = decltype(fc)::value;
+                    general_fl<FL>(fg, pt, mask, &out[slot_a<FL, K>()], &out[slot_b<FL, K>()]);
+                });
+            });
+        }
+        if (u == 0) {
+            // item 0 of this thread is the row pair (0, N/2): its interior evaluation above read the (zero) record of
+            // i = 0 and is replaced by the general one
+            if (j != 0) {
+                Point pt[4];
+                const int mask = general_points<true>(td, table, t, 0, jl, pt);
+                static_for<0, NF>([&](auto fc) {
+                    constexpr int FL = decltype(fc)::value;
+                    general_fl<FL>(fg, pt, mask, &out[slot_a<FL, 0>()], &out[slot_b<FL, 0>()]);
+                });
+            }
+            // self-mirrored butterflies: row B of item K < R0/2 belongs to X (index R0-K, or R0/2 for the row pair
+            // (0, N/2)), row B of item R0/2 + r to Y (index R0-1-r): swap the upper halves accordingly
+            static_for<0, NF>([&](auto fc) {
+                constexpr int FL = decltype(fc)::value;
+                float2 x_hi[R0 / 2], y_hi[R0 / 2];
+                static_for<0, R0 / 2>([&](auto rc) {
+                    constexpr int r = decltype(rc)::value;
+                    x_hi[r] = out[(FL * 2 + 0) * R0 + R0 / 2 + r];
+                    y_hi[r] = out[(FL * 2 + 1) * R0 + R0 / 2 + r];
+                });
+                static_for<0, R0 / 2>([&](auto rc) {
+                    constexpr int r = decltype(rc)::value;  // r-th upper slot, index R0/2 + r
+                    // new X[R0/2] = old Y[R0-1] (item 0);  new X[R0-K] = old Y[R0-1-K], K = 1..R0/2-1
+                    if constexpr (r == 0) out[(FL * 2 + 0) * R0 + R0 / 2] = y_hi[R0 / 2 - 1];
+                    else out[(FL * 2 + 0) * R0 + R0 / 2 + r] = y_hi[r - 1];
+                    // new Y[R0-1-r'] = old X[R0-1-r']
+                    out[(FL * 2 + 1) * R0 + R0 / 2 + r] = x_hi[r];
+                });
+            });
+        }
+        // first Stockham stage (NS = 1: no twiddles) and its store: y[j*R0 + r] = DFT_R0(x[j + r*JN0])[r]
+        static_for<0, NF>([&](auto fc) {
+            constexpr int FL = decltype(fc)::value;
+            static_for<0, 2>([&](auto bc) {
+                constexpr int BF = decltype(bc)::value;
+                float2* x = &out[(FL * 2 + BF) * R0];
+                Dft<R0>::run(x);
+                const int jb = BF == 0 ? u : base2;
+                float2* y = smem + (FL * CP + cp) * LS + pad_idx(jb * R0);
+#pragma unroll
+                for (int r = 0; r < R0; ++r) y[r] = x[r];
+            });
+        });
+    }
+
     // bx: column-pair group, by: field group, bz: item within the chunk
     template <class Exec, class Args>
     static WSO_HD void run(Exec& ex, float2* smem, int bx, int by, int bz, const Args& args) {
@@ -364,7 +568,10 @@ struct Pass1 {
         const float t = item.t;
 
         // ---- request the first row pair's records before anything else ---------------------------------
-        ex.each([&](int tid, ThreadState& st) { prefetch_thread(td, bx, tid, st); });
+        ex.each([&](int tid, ThreadState& st) {
+            if constexpr (kFuse0) prefetch_fused(td, bx, tid, st);
+            else prefetch_thread(td, bx, tid, st);
+        });
 
         // ---- per-frame (cos,sin)(omega_j * t) table: omega takes few distinct values j*omega0 ------
         float2* table = smem + B * LS;
@@ -383,7 +590,8 @@ struct Pass1 {
         // ---- evolve: 4 wave vectors per work item, all NF fields ------------------------------------
 #ifndef WSO_EXP_SKIP_EVOLVE
         ex.each([&](int tid, ThreadState& st) {
-            if (FAST || use_table) evolve_thread<true>(td, table, t, by, smem, bx, tid, st);
+            if constexpr (kFuse0) fused_thread(td, table, t, by, smem, bx, tid, st);
+            else if (FAST || use_table) evolve_thread<true>(td, table, t, by, smem, bx, tid, st);
             else if constexpr (!FAST) evolve_thread<false>(td, table, t, by, smem, bx, tid, st);
         });
 #endif
@@ -391,7 +599,8 @@ struct Pass1 {
 
         // ---- B complex FFTs of length N along m ---------------------------------------------------
 #ifndef WSO_EXP_SKIP_FFT1
-        RunStages<LOGN, B, 0, 1, Exec>::run(ex, smem, args.tw);
+        if constexpr (kFuse0) RunStages<LOGN, B, 1, R0, Exec>::run(ex, smem, args.tw);  // stage 0 ran in registers
+        else RunStages<LOGN, B, 0, 1, Exec>::run(ex, smem, args.tw);
 #endif
         ex.sync();  // the split below reads CP lines per work item
 #ifdef WSO_EXP_SKIP_STORE1
