@@ -13,7 +13,11 @@ for n in 512 1024; do timeout 60 tools/lat_bench $n 2000 >> $OUT/lat_bench.jsonl
 for so in build/variants/libwsocean_n*.so; do
   [ -f $so ] || continue
   name=$(basename $so .so); name=${name#libwsocean_}
-  case $name in n9_*) wl=c4;; n10_*) wl=c2;; n11_*) wl=c3;; *) wl=c2;; esac
+  case $name in n9_lat*) wl=c1;; n9_*) wl=c4;; n10_*) wl=c2;; n11_*) wl=c3;; *) wl=c2;; esac
+  case $name in *lat*)  # single-tile latency through the C ABI with the variant library (RUNPATH yields to LD_LIBRARY_PATH)
+    mkdir -p /tmp/v_$name; ln -sf $PWD/$so /tmp/v_$name/libwsocean.so
+    echo "$name $(LD_LIBRARY_PATH=/tmp/v_$name timeout 60 tools/lat_bench 512 2000)" >> $OUT/lat_bench_variants.txt 2>> $OUT/lat_bench.err;;
+  esac
   WSO_LIB_PATH=$PWD/$so timeout 100 python bench.py --workload $wl --steps 5 --warmup 3 --no-cpu-baseline > $OUT/var_${name}.json 2> $OUT/var_${name}.err
 done
 # W scratch budget per chunk (WSO_W_BUDGET_MB, default 48): tile-frames per launch triple
@@ -23,4 +27,4 @@ if [ "$2" = budget ]; then
     WSO_W_BUDGET_MB=$mb timeout 100 python bench.py --workload $wl --steps 5 --warmup 3 --no-cpu-baseline > $OUT/var_budget_${wl}_${mb}mb.json 2> $OUT/var_budget_${wl}_${mb}mb.err
   done
 fi
-tail -n 3 $OUT/pytest_gpu.log; cat $OUT/lat_bench.jsonl; python tools/summ.py $OUT/bench_c?.json $OUT/var_*.json
+tail -n 3 $OUT/pytest_gpu.log; cat $OUT/lat_bench.jsonl $OUT/lat_bench_variants.txt 2>/dev/null; python tools/summ.py $OUT/bench_c?.json $OUT/var_*.json

@@ -396,21 +396,24 @@ struct Stage {
 };
 
 // Runs stages FIRST..S-1 of Plan<LOGN> on data already in smem (natural order in, natural order out).
-template <int LOGN, int B, int SI, int NS, class Exec>
+// KEEP_LAST: the outputs of the last stage stay in the registers of the thread that computed them (st.v[i*R + r] =
+// X[(tid%G + G*i) + r*N/R] of line tid/G) instead of going back to shared memory - for consumers that only reduce them.
+template <int LOGN, int B, int SI, int NS, class Exec, bool KEEP_LAST = false>
 struct RunStages {
     static WSO_HD void run(Exec& ex, float2* smem, const float2* __restrict__ tw) {
         constexpr int N = 1 << LOGN;
         constexpr int R = Plan<LOGN>::R[SI];
+        constexpr bool kKeep = KEEP_LAST && (SI + 1 == Plan<LOGN>::S);
         using St = Stage<N, B, R, NS>;
         // only the threads of one line have to agree on that line's loads and stores
         ex.each([&](int tid, ThreadState& st) { St::load(smem, tid, st); });
         ex.template sync_group<St::G, St::T>(1);
         ex.each([&](int tid, ThreadState& st) {
             St::twiddle_dft(tw, tid, st);
-            St::store(smem, tid, st);
+            if (!kKeep) St::store(smem, tid, st);
         });
-        ex.template sync_group<St::G, St::T>(1);
-        if constexpr (SI + 1 < Plan<LOGN>::S) RunStages<LOGN, B, SI + 1, NS * R, Exec>::run(ex, smem, tw);
+        if (!kKeep) ex.template sync_group<St::G, St::T>(1);
+        if constexpr (SI + 1 < Plan<LOGN>::S) RunStages<LOGN, B, SI + 1, NS * R, Exec, KEEP_LAST>::run(ex, smem, tw);
     }
 };
 

@@ -714,6 +714,15 @@ struct Pass2 {
     template <class Args>
     static WSO_HD int hl_log(const Args& args) { return SLAB ? LOGN - 1 - args.slab_shift : LOGN - 1; }
 
+    // K2h only reduces the transformed heights: the outputs of the last stage are folded into min/max straight from
+    // the registers (no final store, barrier and re-load: a third of K2h's shared-memory traffic); only the line
+    // that carries rows 0 and N/2 as one complex transform goes through shared memory (it needs mirrored columns).
+#ifdef WSO_EXP_NO_REG_REDUCE
+    static constexpr bool kReduceFromRegs = false;
+#else
+    static constexpr bool kReduceFromRegs = HEIGHT_ONLY && Plan<LOGN>::S > 1 && (G % 2 == 0);
+#endif
+
     // ---- transform phase: first stage straight from global memory (W rows are contiguous), rest in shared memory
     // crank: rank of this CTA in its cluster pair (PAIR only)
     template <class Exec, class Args>
@@ -753,14 +762,58 @@ struct Pass2 {
             St::store(smem, tid, st);
         });
         ex.template sync_group<G, T>(1);
-        if constexpr (Plan<LOGN>::S > 1) RunStages<LOGN, B, 1, R, Exec>::run(ex, smem, args.tw);
+        if constexpr (Plan<LOGN>::S > 1) RunStages<LOGN, B, 1, R, Exec, kReduceFromRegs>::run(ex, smem, args.tw);
     }
 
     // ---- K2h: min/max of the height = Re of packed field 0
     template <class Exec, class Args>
-    static WSO_HD void reduce_heights(Exec& ex, const float2* smem, int bx, int bz, const Args& args) {
+    static WSO_HD void reduce_heights(Exec& ex, float2* smem, int bx, int bz, const Args& args) {
         const BatchItem item = args.items[bz];
         const int hlog = hl_log(args);
+        if constexpr (kReduceFromRegs) {
+            constexpr int RL = Plan<LOGN>::R[Plan<LOGN>::S - 1];  // radix of the last stage
+            constexpr int NSL = N / RL;                            // its output stride: st.v[i*RL + r] = X[j_i + r*NSL]
+            using StL = Stage<N, B, RL, NSL>;
+            const int mp0 = (SLAB ? (args.slab_rank << hlog) : 0) + bx * RI;  // row item of this CTA's first line
+            const bool has_special = (mp0 == 0);                              // CTA-uniform
+            ex.each([&](int tid, ThreadState& st) {
+                const int ri = tid / GI, lt = tid % GI;
+                const int mp = mp0 + ri;
+                if (mp != 0) {
+                    // column c = lt + G*i + r*NSL: G and NSL are even, so (-1)^(row+col) is one sign per thread
+                    const float s = ((mp + lt) & 1) ? -1.0f : 1.0f;
+                    float mn = kInitMin, mx = kInitMax;
+#pragma unroll
+                    for (int k = 0; k < kValsPerThread; ++k) {
+                        const float h = rmul(st.v[k].x, s);
+                        mn = h < mn ? h : mn;
+                        mx = h > mx ? h : mx;
+                    }
+                    st.v[0] = make_float2(mn, mx);
+                } else {
+                    StL::store(smem, tid, st);
+                }
+            });
+            if (has_special) {
+                ex.template sync_group<G, T>(1);
+                ex.each([&](int tid, ThreadState& st) {
+                    const int ri = tid / GI, lt = tid % GI;
+                    if (mp0 + ri != 0) return;
+                    const float2* l0 = smem + ri * LS;
+                    float mn = kInitMin, mx = kInitMax;
+                    const float s = (lt & 1) ? -1.0f : 1.0f;
+                    for (int c = lt; c < N; c += GI) {
+                        const float2 a = l0[pad_idx(c)], m = l0[pad_idx((N - c) & (N - 1))];
+                        const float hA = rmul(0.5f * (a.x + m.x), s), hB = rmul(0.5f * (a.y + m.y), s);
+                        mn = hA < mn ? hA : mn; mx = hA > mx ? hA : mx;
+                        mn = hB < mn ? hB : mn; mx = hB > mx ? hB : mx;
+                    }
+                    st.v[0] = make_float2(mn, mx);
+                });
+            }
+            ex.commit_minmax(args.minmax + 2 * item.slot);
+            return;
+        }
         ex.each([&](int tid, ThreadState& st) {
             float mn = kInitMin, mx = kInitMax;
             const int ri = tid / GI, lt = tid % GI;
