@@ -35,6 +35,10 @@ def lib():
     return _lib
 
 
+# sizes whose first Stockham radix is 2, 4 or 8 (Plan<LOGN> in wso_device.cuh) store W in the paired layout
+PAIRED_W_LOGN = {5, 6, 7, 9, 10, 11, 13, 14}
+
+
 def compute(n, tile_length, lam, h0_re, h0_im, omega, t, variant=0, want_w=False, anim_period=200.0):
     """Run emulated K1+K2+K3 for one tile-frame. h0_* are (N,N) row-major [m][n] (reference layout).
     anim_period=None forces the direct sincosf path; otherwise the sincos table is used when omega allows."""
@@ -56,6 +60,9 @@ def compute(n, tile_length, lam, h0_re, h0_im, omega, t, variant=0, want_w=False
                                p(norm), p(mm), p(a), p(w))
     if rc != 0:
         raise ValueError(f"no emulated configuration for logn={logn} variant={variant}")
+    if w is not None and logn in PAIRED_W_LOGN:
+        # paired W layout (WLayout<LOGN>::paired in wso_kernels.cuh): element 2*j + half -> canonical half*N/2 + j
+        w = np.concatenate([w[:, :, 0::2], w[:, :, 1::2]], axis=2)
     return a[0], disp, norm, mm[0], mm[1], w
 
 

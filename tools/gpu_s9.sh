@@ -27,4 +27,12 @@ if [ "$2" = budget ]; then
     WSO_W_BUDGET_MB=$mb timeout 100 python bench.py --workload $wl --steps 5 --warmup 3 --no-cpu-baseline > $OUT/var_budget_${wl}_${mb}mb.json 2> $OUT/var_budget_${wl}_${mb}mb.err
   done
 fi
+# DRAM traffic per launch with the caches left alone between kernels (ncu's default flushes them, which hides whether
+# W really stays in L2 between K1 and K2h/K2): two metrics = one pass, no replay
+if [ "$2" = traffic -o "$3" = traffic ]; then
+  for wl in c2 c3 c4; do
+    timeout 150 ncu --cache-control none --clock-control none --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum \
+      -k regex:wso_ -s 45 -c 36 --csv --log-file $OUT/traffic_$wl.csv python bench.py --workload $wl --steps 2 --warmup 3 --no-cpu-baseline > $OUT/traffic_$wl.log 2>&1
+  done
+fi
 tail -n 3 $OUT/pytest_gpu.log; cat $OUT/lat_bench.jsonl $OUT/lat_bench_variants.txt 2>/dev/null; python tools/summ.py $OUT/bench_c?.json $OUT/var_*.json

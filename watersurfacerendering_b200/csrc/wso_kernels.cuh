@@ -82,6 +82,22 @@ using LaunchArgs = LaunchArgsT<kMaxChunk>;
 static constexpr int kSmallChunk = 4;
 using LaunchArgsSmall = LaunchArgsT<kSmallChunk>;
 
+// Layout of the intermediate W of one tile-frame (not slab-decomposed), complex [m'][f][N]:
+//   paired  : element 2*j + half  - the two columns (n = j, n = N-j) that K1 separates out of one complex transform
+//             sit next to each other: K1 stores them as ONE 16-byte word, and K2/K2h fetch both inputs of a
+//             first-stage butterfly pair (u, JN0-u) with one 16-byte load
+//   legacy  : element half*N/2 + j (two 8-byte stores N/2 apart; sizes whose first radix is 16 keep it, their K2
+//             threads own a single first-stage butterfly)
+// half 0: column n = j; half 1: n = N-j (n = N/2 for j = 0).
+template <int LOGN>
+struct WLayout {
+#ifdef WSO_EXP_LEGACY_W
+    static constexpr bool paired = false;
+#else
+    static constexpr bool paired = Plan<LOGN>::S > 1 && Plan<LOGN>::R[0] <= 8;
+#endif
+};
+
 // reference: WSTessendorf.cpp:289-290 — max starts at FLT_MIN (smallest positive), min at FLT_MAX
 static constexpr float kInitMax = 1.17549435e-38f;
 static constexpr float kInitMin = 3.402823466e+38f;
@@ -661,6 +677,9 @@ struct Pass1 {
                     float2* dst = args.Wdst[mp >> hl_log] + ((size_t)((mp & (Hl - 1)) * 4 + f) * 2) * Hl + jl;
                     dst[0] = wa;
                     dst[Hl] = wb;
+                } else if constexpr (WLayout<LOGN>::paired) {
+                    float4* dst = reinterpret_cast<float4*>(Wit + ((size_t)mp * 4 + f) * N) + jl;
+                    *dst = make_float4(wa.x, wa.y, wb.x, wb.y);
                 } else {
                     float2* dst = Wit + ((size_t)mp * 4 + f) * N + jl;
                     dst[0] = wa;
@@ -738,6 +757,61 @@ struct Pass2 {
         constexpr int R = Plan<LOGN>::R[0];
         using St = Stage<N, B, R, 1>;
         const int hlog = hl_log(args);
+        if constexpr (!SLAB && WLayout<LOGN>::paired) {
+            // Paired layout: a thread owns first-stage butterfly PAIRS (p, JN-p) - the mirror column N-n of every
+            // column n of butterfly p belongs to butterfly JN-p - so each 16-byte word (column n, column N-n) feeds
+            // one input of each.  Pair 0 is the two self-mirrored butterflies (0, JN/2); its upper halves are
+            // re-slotted exactly as in K1's fused front end.
+            constexpr int JN = N / R;
+            constexpr int NP = kValsPerThread / (2 * R);  // butterfly pairs per thread
+            static_assert(NP >= 1 && G * NP == JN / 2, "paired first stage: bad shape");
+            ex.each([&](int tid, ThreadState& st) {
+                const int line = tid / G, lt = tid % G;
+                const int ml = bx * RI + line / LPC;
+                const int f = HEIGHT_ONLY ? 0 : by * 2 + (PAIR ? crank : line % LPC);
+                const float4* src = reinterpret_cast<const float4*>(Wit + ((size_t)ml * 4 + f) * N);
+                float2* y = smem + line * LS;
+                static_for<0, NP>([&](auto ic) {
+                    constexpr int I = decltype(ic)::value;
+                    const int p = lt + G * I;
+                    const int base2 = p ? JN - p : JN / 2;
+                    float2* v = &st.v[I * 2 * R];  // v[bf*R + idx]
+                    static_for<0, R>([&](auto kc) {
+                        constexpr int K = decltype(kc)::value;
+                        const int n = K < R / 2 ? p + K * JN : base2 + (K - R / 2) * JN;
+                        const float4 q = src[n];
+                        constexpr int sa = K < R / 2 ? K : R + (K - R / 2);
+                        constexpr int sb = K < R / 2 ? R + (R - 1 - K) : (R - 1 - (K - R / 2));
+                        v[sa] = make_float2(q.x, q.y);
+                        v[sb] = make_float2(q.z, q.w);
+                    });
+                    if (p == 0) {
+                        float2 x_hi[R / 2], y_hi[R / 2];
+                        static_for<0, R / 2>([&](auto rc) {
+                            constexpr int r = decltype(rc)::value;
+                            x_hi[r] = v[R / 2 + r];
+                            y_hi[r] = v[R + R / 2 + r];
+                        });
+                        static_for<0, R / 2>([&](auto rc) {
+                            constexpr int r = decltype(rc)::value;
+                            if constexpr (r == 0) v[R / 2] = y_hi[R / 2 - 1];
+                            else v[R / 2 + r] = y_hi[r - 1];
+                            v[R + R / 2 + r] = x_hi[r];
+                        });
+                    }
+                    static_for<0, 2>([&](auto bc) {
+                        constexpr int BF = decltype(bc)::value;
+                        Dft<R>::run(&v[BF * R]);
+                        float2* yb = y + pad_idx((BF == 0 ? p : base2) * R);
+#pragma unroll
+                        for (int r = 0; r < R; ++r) yb[r] = v[BF * R + r];
+                    });
+                });
+            });
+            ex.template sync_group<G, T>(1);
+            if constexpr (Plan<LOGN>::S > 1) RunStages<LOGN, B, 1, R, Exec, kReduceFromRegs>::run(ex, smem, args.tw);
+            return;
+        }
         ex.each([&](int tid, ThreadState& st) {
             const int line = tid / G;
             const int ml = bx * RI + line / LPC;
