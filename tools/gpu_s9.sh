@@ -22,7 +22,7 @@ for so in build/variants/libwsocean_n*.so; do
 done
 # W scratch budget per chunk (WSO_W_BUDGET_MB, default 48): tile-frames per launch triple
 if [ "$2" = budget ]; then
-  for cfg in c2:16 c2:32 c2:64 c2:96 c3:128 c3:192 c4:24 c4:96; do
+  for cfg in c2:32 c2:48 c2:96 c3:128 c4:32 c4:48 c4:128; do
     wl=${cfg%%:*}; mb=${cfg##*:}
     WSO_W_BUDGET_MB=$mb timeout 100 python bench.py --workload $wl --steps 5 --warmup 3 --no-cpu-baseline > $OUT/var_budget_${wl}_${mb}mb.json 2> $OUT/var_budget_${wl}_${mb}mb.err
   done

@@ -82,6 +82,23 @@ WSO_HD float2 cmul(float2 a, float2 b) {
 #endif
 WSO_HD float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 
+// Cache policy of the two big streams (measured with `ncu --cache-control none`, profiles/r1n_traffic.md: with plain
+// stores the 32 B/pt of map output pushed 60 % of the intermediate W out of the 126 MB L2 before K2 re-read it).
+//   st_stream: the output maps are written once and not read again by this library -> evict-first
+//   ld_last  : K2 is the last reader of W -> the line may go as soon as it has been read
+#if defined(__CUDA_ARCH__) && !defined(WSO_EXP_NO_STREAM_STORES)
+WSO_HD void st_stream(float4* p, float4 v) { __stcs(p, v); }
+#else
+WSO_HD void st_stream(float4* p, float4 v) { *p = v; }
+#endif
+#if defined(__CUDA_ARCH__) && defined(WSO_EXP_LAST_USE_LOADS)
+WSO_HD float4 ld_last(const float4* p) { return __ldlu(p); }
+WSO_HD float2 ld_last(const float2* p) { return __ldlu(p); }
+#else
+WSO_HD float4 ld_last(const float4* p) { return *p; }
+WSO_HD float2 ld_last(const float2* p) { return *p; }
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // Shared-memory line layout: logical element i of an FFT line lives at pad_idx(i).
 // One float2 of padding per 16 elements makes every access pattern of the Stockham stages below

@@ -779,7 +779,7 @@ struct Pass2 {
                     static_for<0, R>([&](auto kc) {
                         constexpr int K = decltype(kc)::value;
                         const int n = K < R / 2 ? p + K * JN : base2 + (K - R / 2) * JN;
-                        const float4 q = src[n];
+                        const float4 q = HEIGHT_ONLY ? src[n] : ld_last(src + n);  // K2 is W's last reader
                         constexpr int sa = K < R / 2 ? K : R + (K - R / 2);
                         constexpr int sb = K < R / 2 ? R + (R - 1 - K) : (R - 1 - (K - R / 2));
                         v[sa] = make_float2(q.x, q.y);
@@ -946,8 +946,8 @@ struct Pass2 {
                     const int cm = (N - c) & (N - 1);   // row N-m' is the conjugate mirror of row m'
                     const float y = rmul(rmul(a0.x, s), inv_amp);
                     const float x = rmul(sl, a0.y), z = rmul(sl, a1.y);
-                    if (rows & 1) outA[c] = make_float4(x, y, z, 1.0f);
-                    if (rows & 2) outB[cm] = make_float4(-x, y, -z, 1.0f);
+                    if (rows & 1) st_stream(&outA[c], make_float4(x, y, z, 1.0f));
+                    if (rows & 2) st_stream(&outB[cm], make_float4(-x, y, -z, 1.0f));
                 }
             } else {
 #pragma unroll kPackUnroll
@@ -957,8 +957,8 @@ struct Pass2 {
                     const float2 a0 = l0[e], a1 = l1[e];
                     const int cm = (N - c) & (N - 1);
                     const float4 ta = make_float4(s * a0.y, s * a1.y, s * a0.x, s * a1.x);
-                    if (rows & 1) outA[c] = ta;
-                    if (rows & 2) outB[cm] = make_float4(-ta.x, -ta.y, ta.z, ta.w);
+                    if (rows & 1) st_stream(&outA[c], ta);
+                    if (rows & 2) st_stream(&outB[cm], make_float4(-ta.x, -ta.y, ta.z, ta.w));
                 }
             }
         } else {
@@ -971,11 +971,11 @@ struct Pass2 {
                 const float2 b0 = make_float2(0.5f * (p0.y + m0.y), -0.5f * (p0.x - m0.x));
                 const float2 b1 = make_float2(0.5f * (p1.y + m1.y), -0.5f * (p1.x - m1.x));
                 if (by == 0) {
-                    if (rows & 1) outA[c] = make_float4(rmul(sl, a0.y), rmul(rmul(a0.x, s), inv_amp), rmul(sl, a1.y), 1.0f);
-                    if (rows & 2) outB[c] = make_float4(rmul(sl, b0.y), rmul(rmul(b0.x, s), inv_amp), rmul(sl, b1.y), 1.0f);
+                    if (rows & 1) st_stream(&outA[c], make_float4(rmul(sl, a0.y), rmul(rmul(a0.x, s), inv_amp), rmul(sl, a1.y), 1.0f));
+                    if (rows & 2) st_stream(&outB[c], make_float4(rmul(sl, b0.y), rmul(rmul(b0.x, s), inv_amp), rmul(sl, b1.y), 1.0f));
                 } else {
-                    if (rows & 1) outA[c] = make_float4(s * a0.y, s * a1.y, s * a0.x, s * a1.x);
-                    if (rows & 2) outB[c] = make_float4(s * b0.y, s * b1.y, s * b0.x, s * b1.x);
+                    if (rows & 1) st_stream(&outA[c], make_float4(s * a0.y, s * a1.y, s * a0.x, s * a1.x));
+                    if (rows & 2) st_stream(&outB[c], make_float4(s * b0.y, s * b1.y, s * b0.x, s * b1.x));
                 }
             }
         }
