@@ -82,16 +82,17 @@ WSO_HD float2 cmul(float2 a, float2 b) {
 #endif
 WSO_HD float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 
-// Cache policy of the two big streams (measured with `ncu --cache-control none`, profiles/r1n_traffic.md: with plain
-// stores the 32 B/pt of map output pushed 60 % of the intermediate W out of the 126 MB L2 before K2 re-read it).
-//   st_stream: the output maps are written once and not read again by this library -> evict-first
-//   ld_last  : K2 is the last reader of W -> the line may go as soon as it has been read
+// Cache policy of the two big streams (measured with `ncu --cache-control none`, profiles/r1n_traffic.md and
+// r1o_traffic.md: with plain stores the 32 B/pt of map output pushed 60 % of the intermediate W out of the 126 MB L2
+// before K2 re-read it; with evict-first map stores 32 %).
+//   st_stream: the output maps are written once and not read again by this library -> evict-first (st.global.cs)
+//   ld_last  : K2 is the last reader of W -> the line may go as soon as it has been read (ld.global.lu); +3 % at 1024^2
 #if defined(__CUDA_ARCH__) && !defined(WSO_EXP_NO_STREAM_STORES)
 WSO_HD void st_stream(float4* p, float4 v) { __stcs(p, v); }
 #else
 WSO_HD void st_stream(float4* p, float4 v) { *p = v; }
 #endif
-#if defined(__CUDA_ARCH__) && defined(WSO_EXP_LAST_USE_LOADS)
+#if defined(__CUDA_ARCH__) && !defined(WSO_EXP_NO_LAST_USE_LOADS)
 WSO_HD float4 ld_last(const float4* p) { return __ldlu(p); }
 WSO_HD float2 ld_last(const float2* p) { return __ldlu(p); }
 #else
