@@ -278,3 +278,48 @@ def test_full_size_properties_2048(wso):
         ec = np.exp(2j * np.pi * (mm * c % n) / n)
         val = np.real(er @ H @ ec) * (-1.0 if (r + c) & 1 else 1.0)
         assert abs(height[r, c] - val) < 2e-5 * a, (r, c)
+
+
+def test_maximum_size_properties_8192(wso):
+    """Largest single-device grid (kMaxLogN = 13; first radix 2: paired W layout with four butterfly pairs per K2
+    thread, 69 KB shared-memory lines).  The oracle would need minutes here, so the check is through size-independent
+    properties on a spectrum built by the device-side Prepare(): disp.w == 1, |disp.y| <= 1 with the bound attained,
+    point symmetry of every channel, Parseval on the height field and texels against the direct float64 Fourier sum."""
+    n = 8192
+    t = 7.75
+    with wso.WSTessendorf(n, 1000.0 * n / 512) as ws:
+        ws.PrepareCounterOnDevice(5)
+        h0 = ws.ExportH0()
+        a = float(ws.ComputeWaves(t))
+        d = ws.GetDisplacements().copy()
+        nm = ws.GetNormals().copy()
+    assert np.isfinite(a) and a > 0
+    ph = (h0["omega"] * np.float32(t)).astype(np.float32).astype(np.float64)
+    H = 2.0 * (h0["re"].astype(np.float64) * np.cos(ph) - h0["im"].astype(np.float64) * np.sin(ph))
+    del ph
+
+    def refl(x):
+        return np.roll(x[::-1, ::-1], (1, 1), axis=(0, 1))
+
+    assert np.all(d[..., 3] == 1.0)
+    assert abs(np.abs(d[..., 1]).max() - 1.0) < 1e-6
+    height = d[..., 1].astype(np.float64) * a
+    assert np.abs(height - refl(height)).max() < 4e-5 * a
+    for ch in (d[..., 0], d[..., 2], nm[..., 0], nm[..., 1]):
+        ch = ch.astype(np.float64)
+        assert np.abs(ch + refl(ch)).max() < 4e-5 * np.abs(ch).max()
+    for ch in (nm[..., 2], nm[..., 3]):
+        ch = ch.astype(np.float64)
+        assert np.abs(ch - refl(ch)).max() < 4e-5 * np.abs(ch).max()
+    Y = 0.5 * (H + refl(H))
+    assert abs(np.sum(height ** 2) / (float(n) * n * np.sum(Y ** 2)) - 1.0) < 1e-5
+    del Y
+    rng = np.random.default_rng(1)
+    mm = np.arange(n)
+    for _ in range(8):
+        r, c = int(rng.integers(n)), int(rng.integers(n))
+        er = np.exp(2j * np.pi * (mm * r % n) / n)
+        ec = np.exp(2j * np.pi * (mm * c % n) / n)
+        row = (er.real @ H) + 1j * (er.imag @ H)   # keeps H real: no 1 GB complex copy
+        val = np.real(row @ ec) * (-1.0 if (r + c) & 1 else 1.0)
+        assert abs(height[r, c] - val) < 4e-5 * a, (r, c)

@@ -92,6 +92,12 @@ WSO_HD void st_stream(float4* p, float4 v) { __stcs(p, v); }
 #else
 WSO_HD void st_stream(float4* p, float4 v) { *p = v; }
 #endif
+// ld_ro: spectrum records are read-only for the lifetime of a launch (experiment hook: the non-coherent path)
+#if defined(__CUDA_ARCH__) && defined(WSO_EXP_LDG_RECORDS)
+WSO_HD float4 ld_ro(const float4* p) { return __ldg(p); }
+#else
+WSO_HD float4 ld_ro(const float4* p) { return *p; }
+#endif
 #if defined(__CUDA_ARCH__) && !defined(WSO_EXP_NO_LAST_USE_LOADS)
 WSO_HD float4 ld_last(const float4* p) { return __ldlu(p); }
 WSO_HD float2 ld_last(const float2* p) { return __ldlu(p); }

@@ -477,7 +477,7 @@ struct Pass1 {
             constexpr int K = decltype(kc)::value;
             const int a = K < R0 / 2 ? u + K * JN0 : base2 + (K - R0 / 2) * JN0;
             const float4* rec = td.hs + ((size_t)jl * H + a) * 2;
-            const float4 q0 = rec[0], q1 = rec[1];
+            const float4 q0 = ld_ro(rec), q1 = ld_ro(rec + 1);
             st.v[4 * K + 0] = make_float2(q0.x, q0.y);
             st.v[4 * K + 1] = make_float2(q0.z, q0.w);
             st.v[4 * K + 2] = make_float2(q1.x, q1.y);
@@ -501,8 +501,8 @@ struct Pass1 {
                 } else {
                     const int a = K < R0 / 2 ? u + K * JN0 : base2 + (K - R0 / 2) * JN0;
                     const float4* rec = td.hs + ((size_t)jl * H + a) * 2;
-                    q0[K] = rec[0];
-                    q1[K] = rec[1];
+                    q0[K] = ld_ro(rec);
+                    q1[K] = ld_ro(rec + 1);
                 }
             });
             const float kxA = td.kv[j], kxB = td.kv[N - j];
