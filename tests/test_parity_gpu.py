@@ -171,6 +171,30 @@ def test_batch_matches_single_frames(wso):
         assert_maps_close(ws.copy_map(0, 38), ws.copy_map(1, 38), d_ref, n_ref, "batch frame 36")
 
 
+@pytest.mark.parametrize("n", [512, 1024, 2048])
+def test_bulk_tilings_vs_oracle(wso, n):
+    """The batched (Bulk) CTA tilings of the benchmarked sizes - K1's fused front end at 512^2 (NF4, radix-2 first
+    stage) and 1024^2 (NF2, radix 4), the 1024-thread K1 at 2048^2, the paired W layout - against the oracle.  A launch
+    of a few tile-frames takes the latency tilings instead, so single-frame tests do not reach these kernels at
+    512^2 / 1024^2."""
+    p, o, xi = _oracle_for(n)
+    nframes = 9 if n <= 1024 else 3
+    times = np.array([1.25 + 0.05 * i for i in range(nframes)], np.float32)
+    with wso.WSTessendorf(n, p.tile_length, max_slots=nframes) as ws:
+        ws.PrepareWithGauss(xi)
+        ws.compute_batch(times)
+        a, mn, mx = ws.read_heights(0, nframes)
+        for i in (0, nframes // 2, nframes - 1):
+            a_ref, d_ref, n_ref = o.compute_waves(float(times[i]))
+            assert_maps_close(ws.copy_map(0, i), ws.copy_map(1, i), d_ref, n_ref, f"N={n} bulk frame {i}")
+            assert abs(a[i] - a_ref) <= SCALAR_REL_TOL * a_ref
+        # the single-frame (latency-tiling) path computes the same frame within the gate as well
+        d_b, n_b = ws.copy_map(0, nframes - 1), ws.copy_map(1, nframes - 1)
+        a1 = ws.ComputeWaves(float(times[-1]))
+        assert abs(a1 - a[-1]) <= SCALAR_REL_TOL * a1
+        assert_maps_close(ws.GetDisplacements(), ws.GetNormals(), d_b, n_b, f"N={n} latency vs bulk tiling")
+
+
 def test_independent_tiles_in_one_batch(wso):
     """BASELINE config 4 in miniature: tiles with different wind / seed, batched in one launch."""
     n, ntiles = 128, 5
