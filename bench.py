@@ -224,9 +224,34 @@ def measure_cpu_baseline(wl, budget_s=12.0):
     for i in range(nfr):
         fn(float(t[i % len(t)]))
     dt = time.perf_counter() - t0
-    return {"value": nfr / dt, "unit": "tile-frames/s", "cores": cores, "kind": kind,
-            "ms_per_tile_frame": dt / nfr * 1e3,
-            "sample": f"{nfr} ComputeWaves(t) calls at {wl['n']}^2 after 1 warm-up, {label}"}
+    out = {"value": nfr / dt, "unit": "tile-frames/s", "cores": cores, "kind": kind,
+           "ms_per_tile_frame": dt / nfr * 1e3,
+           "sample": f"{nfr} ComputeWaves(t) calls at {wl['n']}^2 after 1 warm-up, {label}"}
+    out["cpu_fft_sanity"] = scipy_fft_sanity(wl["n"])
+    return out
+
+
+def scipy_fft_sanity(n, budget_s=3.0):
+    """an independent CPU-FFT figure next to the reference arm (whose FFTW is replaced by a shim):
+    seven complex64 ifft2 of N x N with every host core (pocketfft) - the FFT part of one reference ComputeWaves only."""
+    try:
+        import scipy.fft as sf
+    except Exception as e:  # scipy absent: say so instead of failing the bench
+        return {"unavailable": repr(e)}
+    workers = os.cpu_count() or 1
+    rng = np.random.default_rng(0)
+    x = (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))).astype(np.complex64)
+    sf.ifft2(x, workers=workers)
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        for _ in range(7):
+            sf.ifft2(x, workers=workers)
+        reps += 1
+        dt = time.perf_counter() - t0
+        if dt > budget_s or reps >= 50:
+            break
+    return {"what": "7 x scipy.fft.ifft2(complex64) per tile-frame, FFTs only", "workers": workers,
+            "ms_per_tile_frame": dt / reps * 1e3, "tile_frames_per_s": reps / dt}
 
 
 # ----------------------------------------------------------------------------------------------------
