@@ -132,6 +132,9 @@ public:
     void SetAnimationPeriod(float T) { Set([&](wso_params& p) { p.anim_period = T; }); }
     void SetPhillipsConst(float A) { Set([&](wso_params& p) { p.phillips_const = A; }); }
     void SetLambda(float lambda) { Check(wso_set_lambda(m_Ctx, 0, lambda), "wso_set_lambda"); }
+    // Extension (not in the reference class): its compile-time COMPUTE_JACOBIAN switch (WSTessendorf.cpp:421-428, dead
+    // code there) at run time - displacement.w = Jacobian of the horizontal displacement instead of 1.
+    void SetComputeJacobian(bool on) { Check(wso_set_compute_jacobian(m_Ctx, on ? 1 : 0), "wso_set_compute_jacobian"); }
     void SetDamping(float damping) { Set([&](wso_params& p) { p.damping = damping; }); }
 
     // ---- extensions: device pointers for zero-copy consumers (e.g. Vulkan external memory, row f-2)

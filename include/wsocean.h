@@ -78,6 +78,14 @@ WSO_API int wso_set_params(wso_ctx* ctx, uint32_t tile, const wso_params* p);
 /* Replaces: the Get* family (WSTessendorf.h:82-89); wind direction is returned normalised. */
 WSO_API int wso_get_params(const wso_ctx* ctx, uint32_t tile, wso_params* p);
 WSO_API int wso_set_lambda(wso_ctx* ctx, uint32_t tile, float lambda);
+/* Replaces: the compile-time switch COMPUTE_JACOBIAN (WSTessendorf.cpp:158-175, 330-335, 368-377, 421-428; dead code in
+ * the reference - it does not compile there - so this is an extension with no reference output to pin it to, SURVEY
+ * row f-4).  on != 0: every following compute writes displacement.w = J = (1 + l*dxDx)(1 + l*dzDz) - (l*dxDz)(l*dzDx)
+ * (l = lambda, all four derivatives already carrying the (-1)^(m+n) sign) instead of 1.0f; J < 0 marks folded
+ * (foam) texels.  No extra transform: dxDz == dzDx rides in the empty real slot of the packed field that carries Dz.
+ * Tile sizes up to 4096; not available on the slab path.  Default off = the reference's behaviour. */
+WSO_API int wso_set_compute_jacobian(wso_ctx* ctx, int on);
+WSO_API int wso_get_compute_jacobian(const wso_ctx* ctx, int* on);
 
 /* Replaces: WSTessendorf::Prepare() (WSTessendorf.cpp:36-58) — wave vectors, Gaussian array drawn from
  * the C library rand() exactly like glm::gaussRand does (libs/glm/glm/gtc/random.inl:218-232), Phillips

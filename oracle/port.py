@@ -128,6 +128,36 @@ class PortOracle:
         return np.float32(a), disp, norm
 
 
+    def jacobian(self, t: float) -> np.ndarray:
+        """displacement.w under the reference's COMPUTE_JACOBIAN switch -> float32 [N, N].
+
+        PARITY UNPINNED: that switch is dead code in the reference (WSTessendorf.cpp:158-175, 330-335, 368-377, 421-428;
+        it does not compile there: m_dzDisplacementX / m_dxDisplacementZ and their plans are never declared in the
+        header), so there is no reference output to check this restatement against.  It follows the intent of those
+        lines: two more spectra dzDx = (0 + i*kz) * DisplacementX, dxDz = (0 + i*kx) * DisplacementZ (fp32 complex
+        products, cpp:331-334), the same backward transform and sign, and
+        J = (1 + l*s*dxDx)(1 + l*s*dzDz) - (l*s*dxDz)(l*s*dzDx) in fp32 (cpp:422-426)."""
+        n = self.p.tile_size
+        spec = self.spectra(t)
+        k = numpy_wave_numbers(n, self.p.tile_length)
+        ikz = (1j * k[:, None].astype(np.complex64)).astype(np.complex64)
+        ikx = (1j * k[None, :].astype(np.complex64)).astype(np.complex64)
+        dz_dx = (ikz * spec[3]).astype(np.complex64)
+        dx_dz = (ikx * spec[4]).astype(np.complex64)
+
+        def back(x):  # FFTW_BACKWARD, unnormalised, float64 rounded once to fp32 (as oracle/cpu_fft.h does)
+            return (np.fft.ifft2(x.astype(np.complex128)).real * (float(n) * n)).astype(np.float32)
+
+        idx = np.arange(n)
+        sign = np.where(((idx[:, None] + idx[None, :]) & 1) == 1, np.float32(-1), np.float32(1)).astype(np.float32)
+        lam = np.float32(self.p.lam)
+        one = np.float32(1)
+        dxdx, dzdz = back(spec[5]), back(spec[6])
+        a, b = back(dx_dz), back(dz_dx)
+        return ((one + lam * sign * dxdx) * (one + lam * sign * dzdz)
+                - (lam * sign * a) * (lam * sign * b)).astype(np.float32)
+
+
 # ------------------------------------------------------------------------------------------------
 # Independent NumPy restatement
 # ------------------------------------------------------------------------------------------------

@@ -45,13 +45,14 @@ MAX_ABS_TOL = 1e-4
 SCALAR_REL_TOL = 1e-6
 
 
-def assert_maps_close(disp, norm, disp_ref, norm_ref, what=""):
+def assert_maps_close(disp, norm, disp_ref, norm_ref, what="", skip_w=False):
+    """skip_w: the Jacobian switch is on (disp.w carries J, checked by the caller)."""
     for name, got, ref in (("disp", disp, disp_ref), ("norm", norm, norm_ref)):
         for c in range(4):
             g, r = got[..., c], ref[..., c]
             rng = float(r.max() - r.min())
             if name == "disp" and c == 3:
-                assert np.all(g == 1.0), f"{what} disp.w must be exactly 1.0"
+                assert skip_w or np.all(g == 1.0), f"{what} disp.w must be exactly 1.0"
                 continue
             e2 = rel_l2(g, r)
             emax = float(np.max(np.abs(g.astype(np.float64) - r.astype(np.float64))))

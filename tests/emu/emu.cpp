@@ -11,13 +11,16 @@
 
 using namespace wso;
 
-template <int LOGN, int CP, int NF, int RI>
+// JAC: the Jacobian-channel kernels: K1's general body with field 1's real slot filled, K2 with four
+// lines per CTA (by = 0 only).
+template <int LOGN, int CP, int NF, int RI, bool JAC = false>
 static int run_cfg(const float* amp_t, const float* omega_t, const float* kv, float omega0, float lambda,
                    float t, float* disp, float* norm, float* minmax, float* amp_out, float* w_out) {
     constexpr int N = 1 << LOGN, H = N / 2;
-    using P1 = Pass1<LOGN, CP, NF>;
-    using P2 = Pass2<LOGN, RI, false>;
+    using P1 = Pass1<LOGN, CP, NF, false, false, JAC>;
+    using P2 = Pass2<LOGN, JAC ? 1 : RI, false, false, false, JAC>;
     using PH = Pass2<LOGN, RI, true>;
+    constexpr int RI2 = JAC ? 1 : RI;
     std::vector<float2> tw(N);
     for (int k = 0; k < N; ++k) {
         const double a = 2.0 * 3.14159265358979323846 * k / N;
@@ -80,7 +83,7 @@ static int run_cfg(const float* amp_t, const float* omega_t, const float* kv, fl
     {
         // same choice as launch_tiled() in wso_kernels.cu: the lean instantiation when every item qualifies
         using P1F = Pass1<LOGN, CP, NF, false, true>;
-        const bool fast = td.table_len > 0 && td.use_pairs != 0;
+        const bool fast = !JAC && td.table_len > 0 && td.use_pairs != 0;
         std::vector<float2> smem(P1::SMEM_BYTES / sizeof(float2));
         std::vector<ThreadState> st(P1::T);
         for (int by = 0; by < 4 / NF; ++by)
@@ -104,8 +107,8 @@ static int run_cfg(const float* amp_t, const float* omega_t, const float* kv, fl
     {
         std::vector<float2> smem(P2::SMEM_BYTES / sizeof(float2));
         std::vector<ThreadState> st(P2::T);
-        for (int by = 0; by < 2; ++by)
-            for (int bx = 0; bx < H / RI; ++bx) {
+        for (int by = 0; by < (JAC ? 1 : 2); ++by)
+            for (int bx = 0; bx < H / RI2; ++bx) {
                 for (auto& v : smem) v = make_float2(NAN, NAN);
                 HostExec ex{P2::T, st.data()};
                 P2::run(ex, smem.data(), bx, by, 0, args);
@@ -417,5 +420,14 @@ extern "C" int wso_emu_compute(int logn, int variant, const float* amp_t, const 
     CFG(10, 0, 4, 2, 4)
     CFG(11, 0, 4, 1, 2)
 #undef CFG
+    // variants 100+: the Jacobian-channel kernels with the same K1 / K2h tilings
+#define JCFG(L, V, CP, NF, RI) \
+    if (logn == L && variant == 100 + V) return run_cfg<L, CP, NF, RI, true>(amp_t, omega_t, kv, omega0, lambda, t, disp, norm, minmax, amp_out, w_out);
+    JCFG(4, 0, 8, 4, 8)
+    JCFG(6, 1, 4, 2, 2)
+    JCFG(8, 0, 4, 4, 4)
+    JCFG(9, 0, 4, 4, 4)
+    JCFG(10, 0, 4, 2, 4)
+#undef JCFG
     return -1;
 }

@@ -106,3 +106,27 @@ def test_emulated_slab_decomposition_matches_single_device(name, variant, world)
     assert (a, mn, mx) == (a1, mn1, mx1)
     assert disp.tobytes() == d1.tobytes() and norm.tobytes() == n1.tobytes()
     assert_maps_close(disp, norm, g["disp"][i], g["norm"][i], f"{name} slab x{world}")
+
+
+@pytest.mark.parametrize("name,variant", [("n16_default", 100), ("n64_wind", 101), ("n256_default", 100)])
+def test_emulated_jacobian_channel(name, variant):
+    """with the Jacobian switch on, displacement.w = J (oracle restatement of the reference's dead
+    COMPUTE_JACOBIAN lines - parity unpinned, see PortOracle.jacobian) and every other channel is unchanged."""
+    g, params = load_golden(name)
+    h0 = g["h0"]
+    n = params["tile_size"]
+    o = P.PortOracle(P.OceanParams(tile_size=n, tile_length=params["tile_length"], lam=params["lam"]))
+    o.import_h0(h0_struct(h0))
+    for i, t in enumerate(g["t"][:2]):
+        args = (n, params["tile_length"], params["lam"], h0[..., 0], h0[..., 1], h0[..., 4], float(t))
+        a, disp, norm, mn, mx, _ = E.compute(*args, variant=variant, anim_period=params["anim_period"])
+        a0, disp0, norm0, mn0, mx0, _ = E.compute(*args, variant=variant - 100, anim_period=params["anim_period"])
+        assert (a, mn, mx) == (a0, mn0, mx0)
+        assert_maps_close(disp, norm, g["disp"][i], g["norm"][i], f"{name} jacobian t={t}", skip_w=True)
+        # packed fields 0, 2, 3 are untouched: bit-identical; Dz shares its complex transform with the new dzDx
+        # field, so disp.z moves in the last bits only (covered by the gate above)
+        assert np.array_equal(disp[..., :2], disp0[..., :2]) and np.array_equal(norm, norm0)
+        j_ref = o.jacobian(float(t)).astype(np.float64)
+        j = disp[..., 3].astype(np.float64)
+        assert rel_l2(j, j_ref) <= 1e-5
+        assert np.abs(j - j_ref).max() <= 1e-4 * max(j_ref.max() - j_ref.min(), 1e-30)

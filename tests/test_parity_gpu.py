@@ -347,3 +347,43 @@ def test_maximum_size_properties_8192(wso):
         row = (er.real @ H) + 1j * (er.imag @ H)   # keeps H real: no 1 GB complex copy
         val = np.real(row @ ec) * (-1.0 if (r + c) & 1 else 1.0)
         assert abs(height[r, c] - val) < 4e-5 * a, (r, c)
+
+
+@pytest.mark.parametrize("n", [64, 512, 1024])
+def test_jacobian_channel(wso, n):
+    """SURVEY row f-4 (the reference's COMPUTE_JACOBIAN switch, dead code there: parity unpinned, the oracle is the
+    restatement PortOracle.jacobian): with the switch on displacement.w = J, every other channel stays within the gate
+    of the reference maps; off again it is exactly 1.0f.  Single frames and a batch."""
+    p, o, xi = _oracle_for(n)
+    with wso.WSTessendorf(n, p.tile_length, max_slots=3) as ws:
+        ws.PrepareWithGauss(xi)
+        assert ws.GetComputeJacobian() is False
+        ws.SetComputeJacobian(True)
+        assert ws.GetComputeJacobian() is True
+        times = np.array([0.75, 2.5, 31.0], np.float32)
+        ws.compute_batch(times)
+        a, _, _ = ws.read_heights(0, 3)
+        for i in (0, 2):
+            t = float(times[i])
+            a_ref, d_ref, n_ref = o.compute_waves(t)
+            d, nm = ws.copy_map(0, i), ws.copy_map(1, i)
+            assert_maps_close(d, nm, d_ref, n_ref, f"N={n} jacobian t={t}", skip_w=True)
+            assert abs(a[i] - a_ref) <= SCALAR_REL_TOL * a_ref
+            j_ref = o.jacobian(t).astype(np.float64)
+            j = d[..., 3].astype(np.float64)
+            assert rel_l2(j, j_ref) <= 1e-5, f"N={n} J rel-L2 {rel_l2(j, j_ref):.3e}"
+            assert np.abs(j - j_ref).max() <= 1e-4 * (j_ref.max() - j_ref.min())
+        a1 = ws.ComputeWaves(2.5)   # single-frame entry point, same kernels
+        assert np.array_equal(ws.GetDisplacements(), ws.copy_map(0, 1)) and a1 == a[1]
+        ws.SetComputeJacobian(False)
+        ws.ComputeWaves(2.5)
+        assert np.all(ws.GetDisplacements()[..., 3] == 1.0)
+
+
+def test_jacobian_channel_size_limit(wso):
+    from watersurfacerendering_b200 import _lib as L
+    with wso.WSTessendorf(8192, 16000.0) as ws:
+        with pytest.raises(L.WsoError) as e:
+            ws.SetComputeJacobian(True)
+        assert e.value.status == L.WSO_ERR_INVALID_ARG
+        assert ws.GetComputeJacobian() is False

@@ -54,6 +54,8 @@ SYMBOLS = {
     "wso_set_params": (_int, [_vp, _u32, _pp]),
     "wso_get_params": (_int, [_vp, _u32, _pp]),
     "wso_set_lambda": (_int, [_vp, _u32, _f32]),
+    "wso_set_compute_jacobian": (_int, [_vp, _int]),
+    "wso_get_compute_jacobian": (_int, [_vp, _vp]),
     "wso_prepare": (_int, [_vp, _u32, _int, C.c_uint]),
     "wso_prepare_gauss": (_int, [_vp, _u32, _vp]),
     "wso_prepare_gauss_device": (_int, [_vp, _u32, _vp]),

@@ -55,6 +55,7 @@ struct wso_ctx {
     uint32_t max_tiles = 1, max_slots = 1;
     uint32_t chunk = 1;
     bool first_use = true;
+    bool jacobian = false;  // disp.w = Jacobian instead of 1.0f (wso_set_compute_jacobian)
     uint64_t launches = 0;
     std::vector<Tile> tiles;
     // device
@@ -435,7 +436,9 @@ int enqueue_chunk(wso_ctx* c, uint32_t n_items, const uint32_t* tiles, const flo
         c->prof_launches += 1;
         c->prof_items += n_items;
     }
-    cudaError_t e = wso::launch_compute_waves(c->logn, args, (int)n_items, stream, c->first_use, ev);
+    if (c->jacobian && c->logn > wso::kMaxJacobianLogN)
+        return fail(c, WSO_ERR_INVALID_ARG, "the Jacobian channel is available for tile sizes up to 4096");
+    cudaError_t e = wso::launch_compute_waves(c->logn, args, (int)n_items, stream, c->jacobian, ev);
     if (e != cudaSuccess) return fail_cuda(c, e, "kernel launch");
     c->first_use = false;
     c->launches += (uint64_t)wso::kernels_per_launch();
@@ -608,6 +611,20 @@ int wso_get_params(const wso_ctx* c, uint32_t tile, wso_params* p) {
 int wso_set_lambda(wso_ctx* c, uint32_t tile, float lambda) {
     if (!c || tile >= c->max_tiles || !std::isfinite(lambda)) return WSO_ERR_INVALID_ARG;
     c->tiles[tile].params.lambda = lambda;
+    return WSO_OK;
+}
+
+int wso_set_compute_jacobian(wso_ctx* c, int on) {
+    if (!c) return WSO_ERR_INVALID_ARG;
+    if (on && c->logn > wso::kMaxJacobianLogN)
+        return fail(c, WSO_ERR_INVALID_ARG, "the Jacobian channel is available for tile sizes up to 4096");
+    c->jacobian = on != 0;
+    return WSO_OK;
+}
+
+int wso_get_compute_jacobian(const wso_ctx* c, int* on) {
+    if (!c || !on) return WSO_ERR_INVALID_ARG;
+    *on = c->jacobian ? 1 : 0;
     return WSO_OK;
 }
 

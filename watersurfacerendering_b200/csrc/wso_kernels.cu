@@ -75,7 +75,8 @@ constexpr int min_blocks(int threads) { return threads >= 1024 ? 1 : (1024 / thr
 
 // FAST = every item of the launch has the sincos table and the pair-summed records (any Prepare()-built h0): the
 // lean instantiation of K1.  FAST = false serves imported spectra that lack either property.
-template <int LOGN, class TL, class Args, bool FAST>
+// JAC: packed field 1 also carries dzDx (the Jacobian channel); served by the general (FAST = false) body.
+template <int LOGN, class TL, class Args, bool FAST, bool JAC = false>
 __global__ void __launch_bounds__(Pass1<LOGN, TL::CP, TL::NF>::T, min_blocks(Pass1<LOGN, TL::CP, TL::NF>::T))
 wso_pass1_kernel(const __grid_constant__ Args args) {
     extern __shared__ __align__(16) float2 smem[];
@@ -88,7 +89,7 @@ wso_pass1_kernel(const __grid_constant__ Args args) {
         if (lin >= 148u && lin < 296u) __nanosleep(WSO_EXP_STAGGER_K1_NS);
     }
 #endif
-    Pass1<LOGN, TL::CP, TL::NF, false, FAST>::run(ex, smem, blockIdx.x, blockIdx.y, blockIdx.z, args);
+    Pass1<LOGN, TL::CP, TL::NF, false, FAST, JAC>::run(ex, smem, blockIdx.x, blockIdx.y, blockIdx.z, args);
 }
 
 template <int LOGN, class TL, class Args>
@@ -97,6 +98,17 @@ wso_pass2_kernel(const __grid_constant__ Args args) {
     extern __shared__ __align__(16) float2 smem[];
     DeviceExec ex;
     Pass2<LOGN, TL::RI, false>::run(ex, smem, blockIdx.x, blockIdx.y, blockIdx.z, args);
+}
+
+// K2 with the Jacobian channel: one row item (all four packed fields) per CTA, both maps from one CTA.
+// Sizes up to 4096^2 (four lines of shared memory and 4*N/16 <= 1024 threads).
+constexpr bool jacobian_size_ok(int logn) { return logn <= 12; }
+template <int LOGN, class Args>
+__global__ void __launch_bounds__(Pass2<LOGN, 1, false, false, false, true>::T)
+wso_pass2j_kernel(const __grid_constant__ Args args) {
+    extern __shared__ __align__(16) float2 smem[];
+    DeviceExec ex;
+    Pass2<LOGN, 1, false, false, false, true>::run(ex, smem, blockIdx.x, 0, blockIdx.z, args);
 }
 
 // K2h: height extrema (min/max -> amplitude A) ahead of K2, so that K2 writes disp.y already normalised and no
@@ -125,6 +137,37 @@ static cudaError_t launch_pdl(Kern kern, dim3 grid, int threads, int smem, cudaS
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kern, args);
+}
+
+// Jacobian mode: K1 (general body, field 1 with its real slot filled), K2h, K2 with four lines per CTA
+template <int LOGN, class TL, class Args>
+static cudaError_t launch_tiled_jacobian(const Args& args, int n_items, cudaStream_t stream, cudaEvent_t* ev) {
+    if constexpr (!jacobian_size_ok(LOGN)) {
+        return cudaErrorNotSupported;
+    } else {
+        using P1 = Pass1<LOGN, TL::CP, TL::NF>;
+        using PJ = Pass2<LOGN, 1, false, false, false, true>;
+        using PH = Pass2<LOGN, TL::RH, true>;
+        cudaError_t e;
+        e = cudaFuncSetAttribute(wso_pass1_kernel<LOGN, TL, Args, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P1::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(wso_pass2j_kernel<LOGN, Args>, cudaFuncAttributeMaxDynamicSharedMemorySize, PJ::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(wso_heights_kernel<LOGN, TL, Args>, cudaFuncAttributeMaxDynamicSharedMemorySize, PH::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        if (ev) cudaEventRecord(ev[0], stream);
+        e = launch_pdl(wso_pass1_kernel<LOGN, TL, Args, false, true>, dim3(P1::H / TL::CP, 4 / TL::NF, n_items), P1::T,
+                       P1::SMEM_BYTES, stream, args);
+        if (e != cudaSuccess) return e;
+        if (ev) cudaEventRecord(ev[1], stream);
+        e = launch_pdl(wso_heights_kernel<LOGN, TL, Args>, dim3(PH::H / TL::RH, 1, n_items), PH::T, PH::SMEM_BYTES, stream, args);
+        if (e != cudaSuccess) return e;
+        if (ev) cudaEventRecord(ev[2], stream);
+        e = launch_pdl(wso_pass2j_kernel<LOGN, Args>, dim3(PJ::H, 1, n_items), PJ::T, PJ::SMEM_BYTES, stream, args);
+        if (e != cudaSuccess) return e;
+        if (ev) cudaEventRecord(ev[3], stream);
+        return cudaGetLastError();
+    }
 }
 
 template <int LOGN, class TL, class Args>
@@ -172,9 +215,10 @@ static cudaError_t launch_tiled(const Args& args, int n_items, cudaStream_t stre
 }
 
 template <int LOGN>
-static cudaError_t launch_all(const LaunchArgs& args, int n_items, cudaStream_t stream, bool, cudaEvent_t* ev) {
+static cudaError_t launch_all(const LaunchArgs& args, int n_items, cudaStream_t stream, bool jacobian, cudaEvent_t* ev) {
     using B = typename Cfg<LOGN>::Bulk;
     using L = typename Cfg<LOGN>::Lat;
+    if (jacobian) return launch_tiled_jacobian<LOGN, B, LaunchArgs>(args, n_items, stream, ev);
     // few tile-frames in this launch: the Bulk grid of K1 would leave SMs idle -> fine-grained tiling and the
     // small parameter block
     constexpr int bulk_ctas_per_item = ((1 << LOGN) / 2 / B::CP) * (4 / B::NF);
@@ -189,22 +233,22 @@ static cudaError_t launch_all(const LaunchArgs& args, int n_items, cudaStream_t 
 }
 
 cudaError_t launch_compute_waves(int logn, const LaunchArgs& args, int n_items, cudaStream_t stream,
-                                 bool first_use, cudaEvent_t* ev) {
+                                 bool jacobian, cudaEvent_t* ev) {
     switch (logn) {
 // WSO_ONLY_LOGN: tuning builds instantiate a single size (tools/tune_build.sh) to keep compile times short
 #ifdef WSO_ONLY_LOGN
-        case WSO_ONLY_LOGN: return launch_all<WSO_ONLY_LOGN>(args, n_items, stream, first_use, ev);
+        case WSO_ONLY_LOGN: return launch_all<WSO_ONLY_LOGN>(args, n_items, stream, jacobian, ev);
 #else
-        case 4: return launch_all<4>(args, n_items, stream, first_use, ev);
-        case 5: return launch_all<5>(args, n_items, stream, first_use, ev);
-        case 6: return launch_all<6>(args, n_items, stream, first_use, ev);
-        case 7: return launch_all<7>(args, n_items, stream, first_use, ev);
-        case 8: return launch_all<8>(args, n_items, stream, first_use, ev);
-        case 9: return launch_all<9>(args, n_items, stream, first_use, ev);
-        case 10: return launch_all<10>(args, n_items, stream, first_use, ev);
-        case 11: return launch_all<11>(args, n_items, stream, first_use, ev);
-        case 12: return launch_all<12>(args, n_items, stream, first_use, ev);
-        case 13: return launch_all<13>(args, n_items, stream, first_use, ev);
+        case 4: return launch_all<4>(args, n_items, stream, jacobian, ev);
+        case 5: return launch_all<5>(args, n_items, stream, jacobian, ev);
+        case 6: return launch_all<6>(args, n_items, stream, jacobian, ev);
+        case 7: return launch_all<7>(args, n_items, stream, jacobian, ev);
+        case 8: return launch_all<8>(args, n_items, stream, jacobian, ev);
+        case 9: return launch_all<9>(args, n_items, stream, jacobian, ev);
+        case 10: return launch_all<10>(args, n_items, stream, jacobian, ev);
+        case 11: return launch_all<11>(args, n_items, stream, jacobian, ev);
+        case 12: return launch_all<12>(args, n_items, stream, jacobian, ev);
+        case 13: return launch_all<13>(args, n_items, stream, jacobian, ev);
 #endif
         default: return cudaErrorInvalidValue;
     }

@@ -147,10 +147,12 @@ WSO_HD float eval_height(const float4 q, const float2* table, float t) {
 // Even-type (real spectrum) and odd-type (imaginary spectrum i*V) member of packed field F.
 //   F=0: (height, Dx)   F=1: (none, Dz)   F=2: (dxDx, slopeX)   F=3: (dzDz, slopeZ)
 // reference: WSTessendorf.cpp:303-336 (same products in the same order).  ux,uz: WSTessendorf.h:133-136.
-template <int F>
+// JAC (reference COMPUTE_JACOBIAN: WSTessendorf.cpp:330-335): the otherwise empty real slot of packed
+// field 1 carries dzDx = i*kz * Dx = kz*ux*h~ (a real spectrum; dxDz = i*kx * Dz = kx*uz*h~ is the same field).
+template <int F, bool JAC = false>
 WSO_HD void field_values(const Point& p, float* R, float* V) {
     if (F == 0) { *R = p.H;                              *V = rmul(-p.ux, p.H); }
-    if (F == 1) { *R = 0.0f;                             *V = rmul(-p.uz, p.H); }
+    if (F == 1) { *R = JAC ? rmul(p.kz, rmul(p.ux, p.H)) : 0.0f;  *V = rmul(-p.uz, p.H); }
     if (F == 2) { *R = rmul(p.kx, rmul(p.ux, p.H));      *V = rmul(p.kx, p.H); }
     if (F == 3) { *R = rmul(p.kz, rmul(p.uz, p.H));      *V = rmul(p.kz, p.H); }
 }
@@ -159,11 +161,11 @@ WSO_HD void field_values(const Point& p, float* R, float* V) {
 // q = 2*a + b, a = row (mA,mB), b = column (nA,nB).  MASK bit1: the rows mirror into each other (i >= 1);
 // bit0: the columns do (j >= 1).  Used on the index-0 (Nyquist) and N/2 (DC) lines, where the mirror of
 // a point keeps one of its wave numbers; everywhere else pack_interior applies.
-template <int F>
+template <int F, bool JAC = false>
 WSO_HD void pack_general(const Point (&pt)[4], int mask, float2* outA, float2* outB) {
     float R[4], V[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) field_values<F>(pt[q], &R[q], &V[q]);
+    for (int q = 0; q < 4; ++q) field_values<F, JAC>(pt[q], &R[q], &V[q]);
     float z[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -180,13 +182,18 @@ WSO_HD void pack_general(const Point (&pt)[4], int mask, float2* outA, float2* o
 // every packed field depends on h~ only through S = h~(k) + h~(-k):
 //   F0: Z(k) = S/2 * (1 + ux)      F1: Z(k) = S/2 * uz      F2: Z(k) = S/2 * kx*(ux - 1)     F3: same with z
 // and Z(-k) follows by ux -> -ux, kx -> -kx.  s0 = S(mA,nA)/2, s1 = S(mA,nB)/2; (kx,kz,inv) of those two points.
-template <int F>
+template <int F, bool JAC = false>
 WSO_HD void pack_interior(float s0, float kx0, float kz0, float inv0, float s1, float kx1, float kz1, float inv1,
                           float2* outA, float2* outB) {
     float z0, z1, z2, z3;
     if (F == 0) {
         const float a = kx0 * inv0 * s0, b = kx1 * inv1 * s1;
         z0 = s0 + a; z3 = s0 - a; z1 = s1 + b; z2 = s1 - b;
+    } else if (F == 1 && JAC) {
+        // Z(k) = S/2 * (kz*ux + uz); the even part kz*ux keeps its sign under k -> -k, uz flips
+        const float a0 = kz0 * inv0 * s0, a1 = kz1 * inv1 * s1;
+        const float r0 = kz0 * (kx0 * inv0) * s0, r1 = kz1 * (kx1 * inv1) * s1;
+        z0 = r0 + a0; z3 = r0 - a0; z1 = r1 + a1; z2 = r1 - a1;
     } else if (F == 1) {
         z0 = kz0 * inv0 * s0; z3 = -z0; z1 = kz1 * inv1 * s1; z2 = -z1;
     } else if (F == 2) {
@@ -208,7 +215,7 @@ WSO_HD void pack_interior(float s0, float kx0, float kz0, float inv0, float s1, 
 // FAST: the launch guarantees table_len > 0 and use_pairs for every item (any h0 built by Prepare()): the direct
 // sincosf and per-point-record variants of the evolve loop are not instantiated - the kernel's code shrinks from
 // ~170 KB to what the hot path needs (instruction-cache misses showed up as 7 % of K1's stall cycles).
-template <int LOGN, int CP, int NF, bool SLAB = false, bool FAST = false>
+template <int LOGN, int CP, int NF, bool SLAB = false, bool FAST = false, bool JAC = false>
 struct Pass1 {
     static constexpr int N = 1 << LOGN;
     static constexpr int H = N / 2;
@@ -235,19 +242,19 @@ struct Pass1 {
                                           float kxA, float kxB, float kzA, float inv0, float inv1) {
         float2 a, b;
         if (NF == 4 || (NF == 2 && fg == 0) || (NF == 1 && fg == 0)) {
-            pack_interior<0>(s0, kxA, kzA, inv0, s1, kxB, kzA, inv1, &a, &b);
+            pack_interior<0, JAC>(s0, kxA, kzA, inv0, s1, kxB, kzA, inv1, &a, &b);
             put<0>(smem, 0, cp, eA, eB, a, b);
         }
         if (NF == 4 || (NF == 2 && fg == 0) || (NF == 1 && fg == 1)) {
-            pack_interior<1>(s0, kxA, kzA, inv0, s1, kxB, kzA, inv1, &a, &b);
+            pack_interior<1, JAC>(s0, kxA, kzA, inv0, s1, kxB, kzA, inv1, &a, &b);
             put<1>(smem, NF == 1 ? 0 : 1, cp, eA, eB, a, b);
         }
         if (NF == 4 || (NF == 2 && fg == 1) || (NF == 1 && fg == 2)) {
-            pack_interior<2>(s0, kxA, kzA, inv0, s1, kxB, kzA, inv1, &a, &b);
+            pack_interior<2, JAC>(s0, kxA, kzA, inv0, s1, kxB, kzA, inv1, &a, &b);
             put<2>(smem, NF == 4 ? 2 : 0, cp, eA, eB, a, b);
         }
         if (NF == 4 || (NF == 2 && fg == 1) || (NF == 1 && fg == 3)) {
-            pack_interior<3>(s0, kxA, kzA, inv0, s1, kxB, kzA, inv1, &a, &b);
+            pack_interior<3, JAC>(s0, kxA, kzA, inv0, s1, kxB, kzA, inv1, &a, &b);
             put<3>(smem, NF == 4 ? 3 : (NF == 2 ? 1 : 0), cp, eA, eB, a, b);
         }
     }
@@ -277,19 +284,19 @@ struct Pass1 {
         pt[3] = Point{h3, kxB, kzB, rmul(kxB, q3.z), rmul(kzB, q3.z)};
         float2 a, b;
         if (NF == 4 || (NF == 2 && fg == 0) || (NF == 1 && fg == 0)) {
-            pack_general<0>(pt, mask, &a, &b);
+            pack_general<0, JAC>(pt, mask, &a, &b);
             put<0>(smem, 0, cp, eA, eB, a, b);
         }
         if (NF == 4 || (NF == 2 && fg == 0) || (NF == 1 && fg == 1)) {
-            pack_general<1>(pt, mask, &a, &b);
+            pack_general<1, JAC>(pt, mask, &a, &b);
             put<1>(smem, NF == 1 ? 0 : 1, cp, eA, eB, a, b);
         }
         if (NF == 4 || (NF == 2 && fg == 1) || (NF == 1 && fg == 2)) {
-            pack_general<2>(pt, mask, &a, &b);
+            pack_general<2, JAC>(pt, mask, &a, &b);
             put<2>(smem, NF == 4 ? 2 : 0, cp, eA, eB, a, b);
         }
         if (NF == 4 || (NF == 2 && fg == 1) || (NF == 1 && fg == 3)) {
-            pack_general<3>(pt, mask, &a, &b);
+            pack_general<3, JAC>(pt, mask, &a, &b);
             put<3>(smem, NF == 4 ? 3 : (NF == 2 ? 1 : 0), cp, eA, eB, a, b);
         }
     }
@@ -411,29 +418,29 @@ struct Pass1 {
     static WSO_HD void interior_fl(int fg, float s0, float kx0, float kz0, float inv0, float s1, float kx1, float kz1,
                                    float inv1, float2* a, float2* b) {
         if constexpr (NF == 4) {
-            pack_interior<FL>(s0, kx0, kz0, inv0, s1, kx1, kz1, inv1, a, b);
+            pack_interior<FL, JAC>(s0, kx0, kz0, inv0, s1, kx1, kz1, inv1, a, b);
         } else if constexpr (NF == 2) {
-            if (fg == 0) pack_interior<FL>(s0, kx0, kz0, inv0, s1, kx1, kz1, inv1, a, b);
-            else pack_interior<FL + 2>(s0, kx0, kz0, inv0, s1, kx1, kz1, inv1, a, b);
+            if (fg == 0) pack_interior<FL, JAC>(s0, kx0, kz0, inv0, s1, kx1, kz1, inv1, a, b);
+            else pack_interior<FL + 2, JAC>(s0, kx0, kz0, inv0, s1, kx1, kz1, inv1, a, b);
         } else {
-            if (fg == 0) pack_interior<0>(s0, kx0, kz0, inv0, s1, kx1, kz1, inv1, a, b);
-            else if (fg == 1) pack_interior<1>(s0, kx0, kz0, inv0, s1, kx1, kz1, inv1, a, b);
-            else if (fg == 2) pack_interior<2>(s0, kx0, kz0, inv0, s1, kx1, kz1, inv1, a, b);
-            else pack_interior<3>(s0, kx0, kz0, inv0, s1, kx1, kz1, inv1, a, b);
+            if (fg == 0) pack_interior<0, JAC>(s0, kx0, kz0, inv0, s1, kx1, kz1, inv1, a, b);
+            else if (fg == 1) pack_interior<1, JAC>(s0, kx0, kz0, inv0, s1, kx1, kz1, inv1, a, b);
+            else if (fg == 2) pack_interior<2, JAC>(s0, kx0, kz0, inv0, s1, kx1, kz1, inv1, a, b);
+            else pack_interior<3, JAC>(s0, kx0, kz0, inv0, s1, kx1, kz1, inv1, a, b);
         }
     }
     template <int FL>
     static WSO_HD void general_fl(int fg, const Point (&pt)[4], int mask, float2* a, float2* b) {
         if constexpr (NF == 4) {
-            pack_general<FL>(pt, mask, a, b);
+            pack_general<FL, JAC>(pt, mask, a, b);
         } else if constexpr (NF == 2) {
-            if (fg == 0) pack_general<FL>(pt, mask, a, b);
-            else pack_general<FL + 2>(pt, mask, a, b);
+            if (fg == 0) pack_general<FL, JAC>(pt, mask, a, b);
+            else pack_general<FL + 2, JAC>(pt, mask, a, b);
         } else {
-            if (fg == 0) pack_general<0>(pt, mask, a, b);
-            else if (fg == 1) pack_general<1>(pt, mask, a, b);
-            else if (fg == 2) pack_general<2>(pt, mask, a, b);
-            else pack_general<3>(pt, mask, a, b);
+            if (fg == 0) pack_general<0, JAC>(pt, mask, a, b);
+            else if (fg == 1) pack_general<1, JAC>(pt, mask, a, b);
+            else if (fg == 2) pack_general<2, JAC>(pt, mask, a, b);
+            else pack_general<3, JAC>(pt, mask, a, b);
         }
     }
 
@@ -714,11 +721,13 @@ WSO_HD float amplitude_of(float mn, float mx) {
 // PAIR : the two lines of a row item live in the two CTAs of a thread-block cluster (a 16384-point line pair does not
 //        fit one SM's shared memory): each CTA transforms one line, then packs ONE of the two output rows, reading
 //        its partner's line through distributed shared memory.
-template <int LOGN, int RI, bool HEIGHT_ONLY, bool SLAB = false, bool PAIR = false>
+// JAC  : SURVEY row f-4 (reference COMPUTE_JACOBIAN, WSTessendorf.cpp:421-428): one CTA transforms all FOUR packed
+//        fields of a row item (by = 0 only) and writes both maps, disp.w = the Jacobian of the horizontal displacement.
+template <int LOGN, int RI, bool HEIGHT_ONLY, bool SLAB = false, bool PAIR = false, bool JAC = false>
 struct Pass2 {
     static constexpr int N = 1 << LOGN;
     static constexpr int H = N / 2;
-    static constexpr int LPI = HEIGHT_ONLY ? 1 : 2;  // lines per row item
+    static constexpr int LPI = HEIGHT_ONLY ? 1 : (JAC ? 4 : 2);  // lines per row item
     static constexpr int LPC = PAIR ? 1 : LPI;       // ... of which this CTA holds
     static constexpr int B = RI * LPC;
     static constexpr int T = B * N / kValsPerThread;
@@ -729,6 +738,7 @@ struct Pass2 {
     static_assert(T >= 1 && T <= 1024, "bad CTA size");
     static_assert(H % RI == 0, "bad tiling");
     static_assert(!PAIR || (!HEIGHT_ONLY && RI == 1), "cluster pairs: one row item per CTA pair");
+    static_assert(!JAC || (!HEIGHT_ONLY && !SLAB && !PAIR), "Jacobian variant: single-device maps kernel only");
 
     template <class Args>
     static WSO_HD int hl_log(const Args& args) { return SLAB ? LOGN - 1 - args.slab_shift : LOGN - 1; }
@@ -768,7 +778,7 @@ struct Pass2 {
             ex.each([&](int tid, ThreadState& st) {
                 const int line = tid / G, lt = tid % G;
                 const int ml = bx * RI + line / LPC;
-                const int f = HEIGHT_ONLY ? 0 : by * 2 + (PAIR ? crank : line % LPC);
+                const int f = HEIGHT_ONLY ? 0 : (JAC ? line % LPC : by * 2 + (PAIR ? crank : line % LPC));
                 const float4* src = reinterpret_cast<const float4*>(Wit + ((size_t)ml * 4 + f) * N);
                 float2* y = smem + line * LS;
                 static_for<0, NP>([&](auto ic) {
@@ -815,7 +825,7 @@ struct Pass2 {
         ex.each([&](int tid, ThreadState& st) {
             const int line = tid / G;
             const int ml = bx * RI + line / LPC;
-            const int f = HEIGHT_ONLY ? 0 : by * 2 + (PAIR ? crank : line % LPC);
+            const int f = HEIGHT_ONLY ? 0 : (JAC ? line % LPC : by * 2 + (PAIR ? crank : line % LPC));
             const float2* src = Wit + ((size_t)ml * 4 + f) * 2 * ((size_t)1 << hlog);  // [ml][f][half][jl] of source 0
 #pragma unroll
             for (int i = 0; i < St::NB; ++i) {
@@ -981,6 +991,54 @@ struct Pass2 {
         }
     }
 
+    // Jacobian variant: lines l0..l3 = packed fields 0..3 of the row item; writes rows A = m' and B = N-m' of BOTH maps.
+    // reference: WSTessendorf.cpp:421-428  J = (1 + l*s*dxDx)(1 + l*s*dzDz) - (l*s*dxDz)(l*s*dzDx), dxDz == dzDx
+    static WSO_HD float jacobian_of(float lambda, float dxdx, float dzdz, float dzdx) {
+        const float c = rmul(lambda, dzdx);
+        return rsub(rmul(radd(1.0f, rmul(lambda, dxdx)), radd(1.0f, rmul(lambda, dzdz))), rmul(c, c));
+    }
+    template <int STRIDE>
+    static WSO_HD void pack_item_jac(const float2* l0, const float2* l1, const float2* l2, const float2* l3, int mp,
+                                     float4* dA, float4* dB, float4* nA, float4* nB, float lambda, float inv_amp,
+                                     int lt) {
+        const float s = ((mp + lt) & 1) ? -1.0f : 1.0f;
+        const float sl = rmul(s, lambda);
+        if (mp != 0) {
+            for (int c = lt; c < N; c += STRIDE) {
+                const int e = pad_idx(c);
+                const float2 a0 = l0[e], a1 = l1[e], a2 = l2[e], a3 = l3[e];
+                const int cm = (N - c) & (N - 1);
+                const float y = rmul(rmul(a0.x, s), inv_amp);
+                const float x = rmul(sl, a0.y), z = rmul(sl, a1.y);
+                const float j = jacobian_of(lambda, s * a2.x, s * a3.x, s * a1.x);
+                st_stream(&dA[c], make_float4(x, y, z, j));
+                st_stream(&dB[cm], make_float4(-x, y, -z, j));
+                const float4 ta = make_float4(s * a2.y, s * a3.y, s * a2.x, s * a3.x);
+                st_stream(&nA[c], ta);
+                st_stream(&nB[cm], make_float4(-ta.x, -ta.y, ta.z, ta.w));
+            }
+        } else {
+            // rows 0 and N/2 were transformed as one complex line per field: separate them
+            for (int c = lt; c < N; c += STRIDE) {
+                const int e = pad_idx(c), em = pad_idx((N - c) & (N - 1));
+                float2 a[4], b[4];
+                const float2* ls[4] = {l0, l1, l2, l3};
+#pragma unroll
+                for (int f = 0; f < 4; ++f) {
+                    const float2 p = ls[f][e], m = ls[f][em];
+                    a[f] = make_float2(0.5f * (p.x + m.x), 0.5f * (p.y - m.y));
+                    b[f] = make_float2(0.5f * (p.y + m.y), -0.5f * (p.x - m.x));
+                }
+                st_stream(&dA[c], make_float4(rmul(sl, a[0].y), rmul(rmul(a[0].x, s), inv_amp), rmul(sl, a[1].y),
+                                              jacobian_of(lambda, s * a[2].x, s * a[3].x, s * a[1].x)));
+                st_stream(&dB[c], make_float4(rmul(sl, b[0].y), rmul(rmul(b[0].x, s), inv_amp), rmul(sl, b[1].y),
+                                              jacobian_of(lambda, s * b[2].x, s * b[3].x, s * b[1].x)));
+                st_stream(&nA[c], make_float4(s * a[2].y, s * a[3].y, s * a[2].x, s * a[3].x));
+                st_stream(&nB[c], make_float4(s * b[2].y, s * b[3].y, s * b[2].x, s * b[3].x));
+            }
+        }
+    }
+
     // smem_peer: the partner CTA's line (PAIR only; distributed shared memory on the device)
     template <class Exec, class Args>
     static WSO_HD void pack(Exec& ex, const float2* smem, const float2* smem_peer, int bx, int by, int bz, int crank,
@@ -998,6 +1056,19 @@ struct Pass2 {
         }
         const int hlog = hl_log(args);
         const size_t rows_per_slot = SLAB ? ((size_t)2 << hlog) : (size_t)N;
+        if constexpr (JAC) {
+            float4* outd = args.disp + (size_t)item.slot * ((size_t)N * N);
+            float4* outn = args.norm + (size_t)item.slot * ((size_t)N * N);
+            ex.each([&](int tid, ThreadState&) {
+                const int ri = tid / GI, lt = tid % GI;
+                const int mp = bx * RI + ri;
+                const float2* l0 = smem + (ri * 4) * LS;
+                const size_t ra = (size_t)mp * N, rb = (size_t)(mp == 0 ? H : N - mp) * N;
+                pack_item_jac<GI>(l0, l0 + LS, l0 + 2 * LS, l0 + 3 * LS, mp, outd + ra, outd + rb, outn + ra, outn + rb,
+                                  lambda, inv_amp, lt);
+            });
+            return;
+        }
         float4* out = (by == 0 ? args.disp : args.norm) + (size_t)item.slot * (rows_per_slot * N);
         ex.each([&](int tid, ThreadState&) {
             const int ri = tid / GI, lt = tid % GI;

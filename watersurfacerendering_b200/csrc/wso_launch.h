@@ -15,8 +15,11 @@ static constexpr int kMaxLogN = 13;  // 8192 (single-CTA line transforms; larger
 // Enqueue K1 (evolve + first transform), K2h (height extrema) and K2 (second transform + pack) for
 // n_items tile-frames described by args.items[0..n_items).
 // ev: NULL, or 4 events recorded before K1, between the kernels and after K2 (opt-in profiling).
+// jacobian: write disp.w = Jacobian of the horizontal displacement (sizes up to 4096^2, else
+// cudaErrorNotSupported) instead of the reference default 1.0f.
 cudaError_t launch_compute_waves(int logn, const LaunchArgs& args, int n_items, cudaStream_t stream,
-                                 bool first_use, cudaEvent_t* ev);
+                                 bool jacobian, cudaEvent_t* ev);
+static constexpr int kMaxJacobianLogN = 12;
 int kernels_per_launch();
 
 // Slab-decomposed path (one grid over several devices).  phase 0: K1 on this device's column pairs,

@@ -143,6 +143,16 @@ class WSTessendorf:
     def SetDamping(self, d: float, tile=0): L.check(self._set(tile, damping=float(d)), self._h)
     def SetLambda(self, lam: float, tile=0): L.check(self._lib.wso_set_lambda(self._h, tile, float(lam)), self._h)
 
+    def SetComputeJacobian(self, on: bool = True):
+        """The reference's COMPUTE_JACOBIAN switch (WSTessendorf.cpp:421-428, dead code there) at run time:
+        displacement.w = Jacobian of the horizontal displacement instead of 1."""
+        L.check(self._lib.wso_set_compute_jacobian(self._h, 1 if on else 0), self._h)
+
+    def GetComputeJacobian(self) -> bool:
+        v = C.c_int()
+        L.check(self._lib.wso_get_compute_jacobian(self._h, C.byref(v)), self._h)
+        return bool(v.value)
+
     # ------------------------------------------------------------------ prepare
     def Prepare(self, seed: Optional[int] = None, tile: int = 0):
         """reference Prepare(); ``seed`` = srand(seed) first (the reference app seeds with the clock)."""
