@@ -148,13 +148,19 @@ static cudaError_t launch_tiled_jacobian(const Args& args, int n_items, cudaStre
         using P1 = Pass1<LOGN, TL::CP, TL::NF>;
         using PJ = Pass2<LOGN, 1, false, false, false, true>;
         using PH = Pass2<LOGN, TL::RH, true>;
+        static bool configured[16] = {};  // per device: opt in to > 48 KB of dynamic shared memory once
+        int dev = 0;
+        cudaGetDevice(&dev);
         cudaError_t e;
-        e = cudaFuncSetAttribute(wso_pass1_kernel<LOGN, TL, Args, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P1::SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(wso_pass2j_kernel<LOGN, Args>, cudaFuncAttributeMaxDynamicSharedMemorySize, PJ::SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(wso_heights_kernel<LOGN, TL, Args>, cudaFuncAttributeMaxDynamicSharedMemorySize, PH::SMEM_BYTES);
-        if (e != cudaSuccess) return e;
+        if (dev < 0 || dev >= 16 || !configured[dev]) {
+            e = cudaFuncSetAttribute(wso_pass1_kernel<LOGN, TL, Args, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P1::SMEM_BYTES);
+            if (e != cudaSuccess) return e;
+            e = cudaFuncSetAttribute(wso_pass2j_kernel<LOGN, Args>, cudaFuncAttributeMaxDynamicSharedMemorySize, PJ::SMEM_BYTES);
+            if (e != cudaSuccess) return e;
+            e = cudaFuncSetAttribute(wso_heights_kernel<LOGN, TL, Args>, cudaFuncAttributeMaxDynamicSharedMemorySize, PH::SMEM_BYTES);
+            if (e != cudaSuccess) return e;
+            if (dev >= 0 && dev < 16) configured[dev] = true;
+        }
         if (ev) cudaEventRecord(ev[0], stream);
         e = launch_pdl(wso_pass1_kernel<LOGN, TL, Args, false, true>, dim3(P1::H / TL::CP, 4 / TL::NF, n_items), P1::T,
                        P1::SMEM_BYTES, stream, args);
