@@ -5,6 +5,7 @@
 TAG=${1:-r1h}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
+[ -x tools/lat_bench ] || make -C examples lat_bench > /dev/null 2>&1
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/smi.txt 2>&1
 nproc > $OUT/host.txt; grep -m1 'model name' /proc/cpuinfo >> $OUT/host.txt
 timeout 420 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_gpu.log

@@ -4,6 +4,7 @@
 TAG=${1:-r1i}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
+[ -x tools/lat_bench ] || make -C examples lat_bench > /dev/null 2>&1
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/smi.txt 2>&1
 timeout 420 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_gpu.log
 for wl in c2 c3 c4 c1; do
