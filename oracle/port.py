@@ -128,7 +128,7 @@ class PortOracle:
         return np.float32(a), disp, norm
 
 
-    def jacobian(self, t: float) -> np.ndarray:
+    def jacobian(self, t: float, parts: bool = False):
         """displacement.w under the reference's COMPUTE_JACOBIAN switch -> float32 [N, N].
 
         PARITY UNPINNED: that switch is dead code in the reference (WSTessendorf.cpp:158-175, 330-335, 368-377, 421-428;
@@ -154,8 +154,11 @@ class PortOracle:
         one = np.float32(1)
         dxdx, dzdz = back(spec[5]), back(spec[6])
         a, b = back(dx_dz), back(dz_dx)
-        return ((one + lam * sign * dxdx) * (one + lam * sign * dzdz)
-                - (lam * sign * a) * (lam * sign * b)).astype(np.float32)
+        j = ((one + lam * sign * dxdx) * (one + lam * sign * dzdz)
+             - (lam * sign * a) * (lam * sign * b)).astype(np.float32)
+        if parts:  # the four signed derivative fields as well (tests)
+            return j, sign * dxdx, sign * dzdz, sign * a, sign * b
+        return j
 
 
 # ------------------------------------------------------------------------------------------------
