@@ -142,3 +142,57 @@ class EmuSlabBackend:
             rows[ml] = mp
             rows[self.hl + ml] = self.n // 2 if mp == 0 else self.n - mp
         return rows
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# warp-per-line kernels (wso_kernels2.cuh) on the fiber emulator (fiber_simt.h)
+# ---------------------------------------------------------------------------------------------------------------------
+LIB2 = os.path.join(HERE, "libwsoemu2.so")
+_lib2 = None
+
+
+def lib2():
+    global _lib2
+    if _lib2 is None:
+        deps = [os.path.join(HERE, "emu2.cpp"), os.path.join(HERE, "fiber_simt.h"),
+                os.path.join(CSRC, "wso_kernels2.cuh"), os.path.join(CSRC, "wso_simt.cuh"),
+                os.path.join(CSRC, "wso_kernels.cuh"), os.path.join(CSRC, "wso_device.cuh")]
+        if not os.path.exists(LIB2) or any(os.path.getmtime(d) > os.path.getmtime(LIB2) for d in deps):
+            cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+            subprocess.check_call([cxx, "-std=c++17", "-O3", "-w", "-ffp-contract=off", "-fPIC", "-shared",
+                                   "-I", CSRC, "-I", HERE, "-o", LIB2, os.path.join(HERE, "emu2.cpp")])
+        L = C.CDLL(LIB2)
+        vp = C.c_void_p
+        L.wso_emu2_compute.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_float, C.c_float, vp, vp, vp, vp,
+                                       vp, vp]
+        L.wso_emu2_compute.restype = C.c_int
+        _lib2 = L
+    return _lib2
+
+
+def compute2(n, tile_length, lam, h0_re, h0_im, omega, times, variant=0, want_w=False, anim_period=200.0):
+    """Emulated warp-per-line K1 + K2h + K2 for len(times) tile-frames of one tile (one launch, several items).
+    Returns (A[n_items], disp[n_items,N,N,4], norm[...], min[n_items], max[n_items], W or None)."""
+    logn = int(np.log2(n))
+    times = np.ascontiguousarray(np.atleast_1d(np.asarray(times, np.float32)))
+    k = len(times)
+    amp_t = np.ascontiguousarray(np.stack([h0_re.T, h0_im.T], axis=-1).astype(np.float32))
+    om_t = np.ascontiguousarray(omega.T.astype(np.float32))
+    idx = np.arange(n, dtype=np.float32)
+    kv = (np.pi * (np.float32(2) * idx - np.float32(n)).astype(np.float64)
+          / np.float64(np.float32(tile_length))).astype(np.float32)
+    disp = np.zeros((k, n, n, 4), np.float32)
+    norm = np.zeros((k, n, n, 4), np.float32)
+    mm = np.zeros((k, 2), np.float32)
+    a = np.zeros(k, np.float32)
+    w = np.zeros((k, n // 2, 4, n), np.complex64) if want_w else None
+    p = lambda x: None if x is None else x.ctypes.data_as(C.c_void_p)
+    omega0 = float(np.float32(np.float64(np.float32(2.0)) * np.pi / np.float64(np.float32(anim_period))))
+    rc = lib2().wso_emu2_compute(logn, variant, k, p(amp_t), p(om_t), p(kv), omega0, float(lam), p(times), p(disp),
+                                 p(norm), p(mm), p(a), p(w))
+    if rc != 0:
+        raise ValueError(f"emu2: rc={rc} for logn={logn} variant={variant}")
+    if w is not None:
+        # paired W layout: element 2*j + half -> canonical half*N/2 + j
+        w = np.concatenate([w[..., 0::2], w[..., 1::2]], axis=-1)
+    return a, disp, norm, mm[:, 0], mm[:, 1], w

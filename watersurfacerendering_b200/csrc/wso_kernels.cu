@@ -1,6 +1,7 @@
 // wso_kernels.cu — __global__ entry points and launch dispatch for sm_100a.
 #include "wso_launch.h"
 
+#include <cstdlib>
 #include <type_traits>
 
 #include "wso_kernels.cuh"
@@ -139,6 +140,16 @@ static cudaError_t launch_pdl(Kern kern, dim3 grid, int threads, int smem, cudaS
     return cudaLaunchKernelEx(&cfg, kern, args);
 }
 
+// Which of K1 / K2h / K2 run on the warp-per-line kernels when a launch qualifies: all three unless WSO_WARP_CORE says
+// otherwise (a bit mask, 0 = the CTA-per-line kernels of this file; used for A/B measurements).
+static int warp_core_mask() {
+    static const int mask = [] {
+        const char* env = std::getenv("WSO_WARP_CORE");
+        return env ? (std::atoi(env) & 7) : 0;
+    }();
+    return mask;
+}
+
 // Jacobian mode: K1 (general body, field 1 with its real slot filled), K2h, K2 with four lines per CTA
 template <int LOGN, class TL, class Args>
 static cudaError_t launch_tiled_jacobian(const Args& args, int n_items, cudaStream_t stream, cudaEvent_t* ev) {
@@ -205,16 +216,31 @@ static cudaError_t launch_tiled(const Args& args, int n_items, cudaStream_t stre
     bool fast = true;
 #endif
     for (int i = 0; i < n_items; ++i) fast = fast && args.td[i].table_len > 0 && args.td[i].use_pairs != 0;
-    e = fast ? launch_pdl(wso_pass1_kernel<LOGN, TL, Args, true>, g1, P1::T, P1::SMEM_BYTES, stream, args)
-             : launch_pdl(wso_pass1_kernel<LOGN, TL, Args, false>, g1, P1::T, P1::SMEM_BYTES, stream, args);
+    // batched launches of 512^2 / 1024^2 / 2048^2 run on the warp-per-line kernels (wso_kernels2.cu); mask bit k = kernel k
+    int warp_mask = 0;
+    if constexpr (std::is_same<Args, LaunchArgs>::value) {
+        if (fast && warp_core_supported(LOGN)) warp_mask = warp_core_mask();
+    }
+    if constexpr (std::is_same<Args, LaunchArgs>::value) {
+        if (warp_mask & 1) e = launch_warp_core(LOGN, 0, args, n_items, stream);
+    }
+    if (!(warp_mask & 1))
+        e = fast ? launch_pdl(wso_pass1_kernel<LOGN, TL, Args, true>, g1, P1::T, P1::SMEM_BYTES, stream, args)
+                 : launch_pdl(wso_pass1_kernel<LOGN, TL, Args, false>, g1, P1::T, P1::SMEM_BYTES, stream, args);
     if (e != cudaSuccess) return e;
     if (ev) cudaEventRecord(ev[1], stream);
     const dim3 gh(PH::H / TL::RH, 1, n_items);
-    e = launch_pdl(wso_heights_kernel<LOGN, TL, Args>, gh, PH::T, PH::SMEM_BYTES, stream, args);
+    if constexpr (std::is_same<Args, LaunchArgs>::value) {
+        if (warp_mask & 2) e = launch_warp_core(LOGN, 1, args, n_items, stream);
+    }
+    if (!(warp_mask & 2)) e = launch_pdl(wso_heights_kernel<LOGN, TL, Args>, gh, PH::T, PH::SMEM_BYTES, stream, args);
     if (e != cudaSuccess) return e;
     if (ev) cudaEventRecord(ev[2], stream);
     const dim3 g2(P2::H / TL::RI, 2, n_items);
-    e = launch_pdl(wso_pass2_kernel<LOGN, TL, Args>, g2, P2::T, P2::SMEM_BYTES, stream, args);
+    if constexpr (std::is_same<Args, LaunchArgs>::value) {
+        if (warp_mask & 4) e = launch_warp_core(LOGN, 2, args, n_items, stream);
+    }
+    if (!(warp_mask & 4)) e = launch_pdl(wso_pass2_kernel<LOGN, TL, Args>, g2, P2::T, P2::SMEM_BYTES, stream, args);
     if (e != cudaSuccess) return e;
     if (ev) cudaEventRecord(ev[3], stream);
     return cudaGetLastError();

@@ -22,6 +22,12 @@ cudaError_t launch_compute_waves(int logn, const LaunchArgs& args, int n_items, 
 static constexpr int kMaxJacobianLogN = 12;
 int kernels_per_launch();
 
+// Warp-per-line kernels (wso_kernels2.cu): 512^2, 1024^2 and 2048^2, every item with the sincos table and the pair-summed
+// records, no Jacobian channel.  which: 0 = K1, 1 = K2h, 2 = K2 (same W layout and stream protocol as the kernels of
+// wso_kernels.cu, so the two sets can be mixed kernel by kernel).
+bool warp_core_supported(int logn);
+cudaError_t launch_warp_core(int logn, int which, const LaunchArgs& args, int n_items, cudaStream_t stream);
+
 // Slab-decomposed path (one grid over several devices).  phase 0: K1 on this device's column pairs,
 // 1: K2h on its row items, 2: K2 (pair = force the two-CTA cluster variant; always used when a line pair exceeds
 // one SM's shared memory).
