@@ -129,7 +129,11 @@ def cpu_reference_model(wl, fft_fast=True):
     from oracle import port as P
     from oracle import refmodel as R
     n, L = wl["n"], wl["L"]
+    # every host core this process may run on: torch.distributed.run exports OMP_NUM_THREADS=1 to its workers, which
+    # would silently time the reference on one thread
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     if R.available():
+        R.set_threads(ncpu)
         mode = R.FFT_FLOAT32
         label = "reference WSTessendorf.cpp verbatim + shim fp32 FFT (NOT FFTW)"
         try:
@@ -147,6 +151,7 @@ def cpu_reference_model(wl, fft_fast=True):
             m.PrepareWithGauss(gauss(n, wl["seed"] + tile))
             return m.ComputeWaves
         return "reference", label, cores, make
+    P.lib().wso_oracle_set_threads(ncpu)
     cores = int(P.lib().wso_oracle_max_threads())
 
     def make(tile):
@@ -178,6 +183,7 @@ def step_times(wl, step):
 def run_reference_arm(args, wl, rank, world):
     if rank != 0:
         return
+    os.environ.setdefault("OMP_PROC_BIND", "close")  # read when libgomp loads (threads pinned next to each other)
     scale = 1.0
     if wl["n"] > 4096:   # the reference needs ~33 GB and minutes per 16384^2 frame: time 4096^2 and scale by points
         scale = (wl["n"] / 4096) ** 2

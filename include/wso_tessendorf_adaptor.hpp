@@ -8,9 +8,11 @@
 // and src/scene/WSTessendorf.cpp + FFTW are dropped from the build.
 //
 // Differences a caller can observe:
-//   * GetDisplacements()/GetNormals() return a read-only view (data()/size()/begin()/end()/operator[]) over
-//     pinned host memory instead of a const std::vector<vec4>& - the memcpy in
-//     WaterSurfaceMesh::CopyModelTessDataToStagingBuffer (WaterSurfaceMesh.cpp:701-755) works as is.
+//   * none in the signatures: GetDisplacements()/GetNormals() return const std::vector<vec4>& exactly as
+//     WSTessendorf.h:95-101 does.  The vectors are owned here, sized and filled with the reference's defaults in
+//     Prepare() (WSTessendorf.cpp:48-54), page-locked in place (wso_register_host) and written by the device-to-host
+//     copies of every ComputeWaves() - the memcpy in WaterSurfaceMesh::CopyModelTessDataToStagingBuffer
+//     (WaterSurfaceMesh.cpp:701-755) reads them as before;
 //   * errors of the CUDA path throw std::runtime_error (the reference has no failure modes besides asserts).
 // glm is used when the including translation unit has already included <glm/glm.hpp> (as the reference's
 // pch.h does); otherwise two minimal POD vectors stand in so the header is self-contained.
@@ -21,6 +23,7 @@
 #include <cstdint>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 #include "wsocean.h"
 
@@ -54,24 +57,6 @@ public:
     using Displacement = wso_adaptor::vec4;  // RGBA32F texel (VK_FORMAT_R32G32B32A32_SFLOAT)
     using Normal = wso_adaptor::vec4;
 
-    // Read-only view over the pinned host copy of a map; valid until the next ComputeWaves()/Prepare().
-    template <typename T>
-    class MapView {
-    public:
-        MapView() = default;
-        MapView(const T* p, size_t n) : m_Data(p), m_Size(n) {}
-        const T* data() const { return m_Data; }
-        size_t size() const { return m_Size; }
-        bool empty() const { return m_Size == 0; }
-        const T* begin() const { return m_Data; }
-        const T* end() const { return m_Data + m_Size; }
-        const T& operator[](size_t i) const { return m_Data[i]; }
-
-    private:
-        const T* m_Data{nullptr};
-        size_t m_Size{0};
-    };
-
     explicit WSTessendorf(uint32_t tileSize = s_kDefaultTileSize, float tileLength = s_kDefaultTileLength,
                           int cudaDevice = 0) {
         wso_params p;
@@ -81,19 +66,23 @@ public:
         p.tile_length = tileLength;
         Check(wso_create(&p, cudaDevice, 1, 1, &m_Ctx), "wso_create");
     }
-    ~WSTessendorf() { wso_destroy(m_Ctx); }
+    ~WSTessendorf() {
+        ReleaseMaps();
+        wso_destroy(m_Ctx);
+    }
     WSTessendorf(const WSTessendorf&) = delete;
     WSTessendorf& operator=(const WSTessendorf&) = delete;
 
     void Prepare() {
         Check(wso_prepare(m_Ctx, 0, /*reseed=*/0, 0), "wso_prepare");
-        RefreshViews();
+        ResizeMaps();
     }
 
     float ComputeWaves(float time) {
         float amplitude = 0.0f;
-        Check(wso_compute(m_Ctx, time, &amplitude), "wso_compute");
-        Check(wso_read_heights(m_Ctx, 0, 1, nullptr, &m_MinHeight, &m_MaxHeight), "wso_read_heights");
+        Check(wso_compute_to_host(m_Ctx, 1, nullptr, &time, reinterpret_cast<float*>(m_Displacements.data()),
+                                  reinterpret_cast<float*>(m_Normals.data()), &amplitude, &m_MinHeight, &m_MaxHeight),
+              "wso_compute_to_host");
         return amplitude;
     }
 
@@ -113,9 +102,9 @@ public:
     float GetMaxHeight() const { return m_MaxHeight; }
 
     size_t GetDisplacementCount() const { return m_Displacements.size(); }
-    const MapView<Displacement>& GetDisplacements() const { return m_Displacements; }
+    const std::vector<Displacement>& GetDisplacements() const { return m_Displacements; }
     size_t GetNormalCount() const { return m_Normals.size(); }
-    const MapView<Normal>& GetNormals() const { return m_Normals; }
+    const std::vector<Normal>& GetNormals() const { return m_Normals; }
 
     // ---- setters (reference: WSTessendorf.cpp:459-505)
     void SetTileSize(uint32_t size) {
@@ -154,14 +143,31 @@ private:
         f(p);
         Check(wso_set_params(m_Ctx, 0, &p), "wso_set_params");
     }
-    void RefreshViews() {
-        const float* d = nullptr;
-        const float* n = nullptr;
-        size_t cnt = 0;
-        Check(wso_map_host(m_Ctx, WSO_MAP_DISPLACEMENT, &d, &cnt), "wso_map_host");
-        Check(wso_map_host(m_Ctx, WSO_MAP_NORMAL, &n, &cnt), "wso_map_host");
-        m_Displacements = MapView<Displacement>(reinterpret_cast<const Displacement*>(d), cnt);
-        m_Normals = MapView<Normal>(reinterpret_cast<const Normal*>(n), cnt);
+    // reference: Prepare() resizes both maps to N*N texels with default contents (WSTessendorf.cpp:48-54); a resize keeps
+    // what is already there, like std::vector::resize does in the reference
+    void ResizeMaps() {
+        const size_t n = (size_t)GetTileSize() * GetTileSize();
+        if (m_Displacements.size() == n && m_Normals.size() == n && m_Registered) return;
+        ReleaseMaps();
+        Displacement d0;
+        d0.x = d0.y = d0.z = d0.w = 0.0f;
+        Normal n0;
+        n0.x = 0.0f; n0.y = 1.0f; n0.z = 0.0f; n0.w = 0.0f;
+        m_Displacements.resize(n, d0);
+        m_Normals.resize(n, n0);
+        // page-lock the vectors' storage where it lies: the device-to-host copies then run at full PCIe speed
+        m_Registered = wso_register_host(m_Displacements.data(), n * sizeof(Displacement)) == WSO_OK;
+        if (m_Registered && wso_register_host(m_Normals.data(), n * sizeof(Normal)) != WSO_OK) {
+            wso_unregister_host(m_Displacements.data());
+            m_Registered = false;
+        }
+    }
+    void ReleaseMaps() {
+        if (m_Registered) {
+            wso_unregister_host(m_Displacements.data());
+            wso_unregister_host(m_Normals.data());
+            m_Registered = false;
+        }
     }
     void* DevicePtr(int which) const {
         void* p = nullptr;
@@ -175,8 +181,9 @@ private:
     }
 
     wso_ctx* m_Ctx{nullptr};
-    MapView<Displacement> m_Displacements;
-    MapView<Normal> m_Normals;
+    std::vector<Displacement> m_Displacements;
+    std::vector<Normal> m_Normals;
+    bool m_Registered{false};
     float m_MinHeight{-1.0f};  // reference: WSTessendorf.h:226-227
     float m_MaxHeight{1.0f};
 };

@@ -138,6 +138,8 @@ WSO_API int wso_read_heights(wso_ctx* ctx, uint32_t first_slot, uint32_t n, floa
  * RGBA32F texels, row-major [m][n], N*N of them.
  *   displacement = (lambda*Dx, height/A, lambda*Dz, 1)      normal = (dh/dx, dh/dz, dDx/dx, dDz/dz)
  * wso_map_host: pinned host copy of slot 0 written by wso_compute (valid until the next compute/prepare).
+ *   Between Prepare() and the first compute every texel holds the reference's resize() defaults
+ *   (WSTessendorf.cpp:48-54): displacement (0,0,0,0), normal (0,1,0,0) - on the host mirrors and in every device slot.
  * wso_map_device: device pointer of any slot (valid until destroy / tile-size change).
  * wso_copy_map: blocking copy of one slot's map into caller memory. */
 WSO_API int wso_map_host(wso_ctx* ctx, int which, const float** ptr, size_t* texels);
@@ -173,6 +175,18 @@ WSO_API int wso_wait_semaphore(wso_ctx* ctx, int index, uint64_t value);
 WSO_API int wso_set_stream(wso_ctx* ctx, void* cuda_stream);
 WSO_API int wso_alloc_host(size_t bytes, void** ptr);
 WSO_API int wso_free_host(void* ptr);
+/* Page-lock memory the CALLER owns (e.g. the storage of the std::vector<glm::vec4> the reference's accessors hand out,
+ * WSTessendorf.h:95-101) so that wso_compute_to_host copies straight into it at full PCIe speed; unregister before
+ * the memory is freed or reallocated.  Failing to register is not fatal: the copies then go through pageable memory. */
+WSO_API int wso_register_host(void* ptr, size_t bytes);
+WSO_API int wso_unregister_host(void* ptr);
+
+/* Two implementations of the three hot-path kernels exist for 512^2, 1024^2 and 2048^2 batched launches: CTA-per-line
+ * (Stockham stages through shared memory) and warp-per-line (radix-32 register stages, shuffle exchanges, bulk-copy line
+ * pipeline).  They produce the same maps within the parity tolerance and share the intermediate layout.  mask bit 0 / 1 /
+ * 2 puts K1 / K2h / K2 on the warp-per-line set; -1 restores the built-in choice (what measured faster per size).
+ * Process-wide; meant for A/B measurements and for the parity tests, which run both sets. */
+WSO_API int wso_select_kernels(int mask);
 
 /* Introspection used by the benchmark: number of kernels launched so far by this context, the chunk
  * (tile-frames per launch) the batched calls use, and the CTA tiling of the two transform kernels. */

@@ -70,12 +70,13 @@ static bool make_setup(int N, const float* amp_t, const float* omega_t, const fl
 }
 
 // K1 (CP column pairs x NF fields per CTA), K2h and K2 (GPC line groups per CTA, NBX CTAs walking the row items)
-template <int LOGN, int CP, int NF, int GPC, int NBX>
+template <int LOGN, int CP, int NF, int GPC, int NBX, int NBUFH = 1>
 static int run_cfg(int n_items, const float* amp_t, const float* omega_t, const float* kv, float omega0, float lambda,
                    const float* times, float* disp, float* norm, float* minmax, float* amp_out, float* w_out) {
     constexpr int N = 1 << LOGN, H = N / 2;
     using P1 = v2::Pass1W<LOGN, CP, NF>;
     using P2 = v2::Pass2W<LOGN, GPC>;
+    using PH = v2::Pass2W<LOGN, GPC, NBUFH>;  // K2h: one or two line buffers per group
     if (n_items < 1 || n_items > kSmallChunk) return -3;
     Setup s;
     if (!make_setup(N, amp_t, omega_t, kv, omega0, lambda, s)) return -2;
@@ -117,7 +118,7 @@ static int run_cfg(int n_items, const float* amp_t, const float* omega_t, const 
             for (auto& x : smem) x = make_float2(NAN, NAN);
             cta.run([&](int tid) {
                 HostCtx cx(&cta, tid);
-                P2::template run<2>(cx, smem.data(), bx, NBX, n_items, args);
+                PH::template run<2>(cx, smem.data(), bx, NBX, n_items, args);
             });
         }
         for (int map = 0; map < 2; ++map)  // K2
@@ -142,17 +143,17 @@ extern "C" int wso_emu2_compute(int logn, int variant, int n_items, const float*
                                 float* norm, float* minmax, float* amp_out, float* w_out) {
 #define CFG(LG, V, CP, NF, GPC, NBX) \
     if (logn == LG && variant == V)  \
-        return run_cfg<LG, CP, NF, GPC, NBX>(n_items, amp_t, omega_t, kv, omega0, lambda, times, disp, norm, minmax, amp_out, w_out);
-    CFG(9, 0, 4, 4, 8, 3)
-    CFG(9, 1, 8, 2, 4, 5)
+        return run_cfg<LG, CP, NF, GPC, NBX, 1 + (V & 1)>(n_items, amp_t, omega_t, kv, omega0, lambda, times, disp, norm, minmax, amp_out, w_out);
+    CFG(9, 0, 8, 4, 8, 3)
+    CFG(9, 1, 4, 2, 4, 5)
     CFG(9, 2, 2, 1, 2, 7)
     CFG(10, 0, 4, 4, 4, 3)
     CFG(10, 1, 8, 2, 2, 5)
-    CFG(10, 2, 2, 4, 3, 7)
-    CFG(10, 3, 1, 1, 1, 2)
-    CFG(11, 0, 4, 4, 2, 3)
-    CFG(11, 1, 2, 2, 3, 5)
-    CFG(11, 2, 8, 1, 1, 4)
+    CFG(10, 2, 2, 4, 6, 7)
+    CFG(10, 3, 1, 1, 2, 2)
+    CFG(11, 0, 2, 4, 2, 3)
+    CFG(11, 1, 4, 2, 6, 5)
+    CFG(11, 2, 8, 1, 4, 4)
 #undef CFG
     return -1;
 }

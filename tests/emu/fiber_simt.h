@@ -108,6 +108,13 @@ class FiberCta {
     // all `count` participants of `key` must arrive before any continues
     void barrier(int key, int count) {
         Bar& b = bars_[key];
+        // a named barrier in use with one participant count must not be joined with another (the device traps)
+        if (b.arrived > 0 && b.count != count) {
+            fprintf(stderr, "fiber_simt: barrier %d joined with count %d while %d threads wait with count %d\n", key,
+                    count, b.arrived, b.count);
+            abort();
+        }
+        b.count = count;
         if (++b.arrived == count) {
             for (int w : b.waiters) state_[w] = 0;
             b.waiters.clear();
@@ -131,6 +138,7 @@ class FiberCta {
   private:
     struct Bar {
         int arrived = 0;
+        int count = 0;
         std::vector<int> waiters;
     };
     static void entry() {

@@ -67,10 +67,11 @@ def test_warp_core_one_hot_layout():
     n = 512
     p = P.OceanParams(tile_size=n, tile_length=1000.0)
     o = P.PortOracle(p)
-    w0 = np.float32(2.0 * np.pi / 200.0)
+    w0 = np.float32(np.float64(np.float32(2.0)) * np.pi / np.float64(np.float32(200.0)))  # (float)(2.0f * M_PI / T)
     for (m, c) in [(0, 0), (0, 5), (5, 0), (n // 2, 3), (3, n // 2), (n - 1, n - 1), (1, n - 1), (n // 2, n // 2),
                    (7, 9), (0, n // 2), (16, 32), (n - 16, 17), (255, 257), (32, 480)]:
         h0 = np.zeros((n, n), P.H0_DTYPE)
+        h0["omega"] = np.float32(10) * w0  # omega(k) == omega(-k) everywhere: the pair-summed records apply
         h0[m, c] = (0.7, -0.3, 0.7, 0.3, np.float32(10) * w0)
         o.import_h0(h0)
         a_ref, d_ref, n_ref = o.compute_waves(3.0)

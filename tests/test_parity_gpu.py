@@ -111,8 +111,20 @@ def test_parameter_variants(wso, kw):
         ws.PrepareWithGauss(xi)
         assert ws.ExportH0().tobytes() == o.h0.tobytes()
         a_ref, d_ref, n_ref = o.compute_waves(9.75)
-        if not np.isfinite(a_ref) or a_ref < 1e-30:
-            pytest.skip("degenerate ocean (reference divides by A = 0)")
+        if a_ref < 1e-30:
+            # Flat ocean (every h0 underflows to 0): the one input where the reference's start values decide the result.
+            # masterMax starts at FLT_MIN - the smallest POSITIVE float, not the lowest (WSTessendorf.cpp:289) - so with
+            # all heights 0 the reference returns A = max(|0|, |FLT_MIN|) = FLT_MIN, min 0, max FLT_MIN, and
+            # NormalizeHeights (cpp:443-455) multiplies the zero heights by 1/FLT_MIN: still 0, no NaN.
+            flt_min = np.float32(1.17549435e-38)
+            assert np.float32(a_ref) == flt_min, "oracle: A must be FLT_MIN on a flat ocean"
+            a = ws.ComputeWaves(9.75)
+            assert np.float32(a) == flt_min
+            assert np.float32(ws.GetMinHeight()) == np.float32(0.0) and np.float32(ws.GetMaxHeight()) == flt_min
+            d, nm = ws.GetDisplacements(), ws.GetNormals()
+            assert np.all(d[..., :3] == 0.0) and np.all(d[..., 3] == 1.0) and np.all(nm == 0.0)
+            assert np.all(d_ref[..., :3] == 0.0) and np.all(n_ref == 0.0)
+            return
         _check_frame(ws, o, 9.75, str(kw))
 
 
@@ -193,6 +205,54 @@ def test_bulk_tilings_vs_oracle(wso, n):
         a1 = ws.ComputeWaves(float(times[-1]))
         assert abs(a1 - a[-1]) <= SCALAR_REL_TOL * a1
         assert_maps_close(ws.GetDisplacements(), ws.GetNormals(), d_b, n_b, f"N={n} latency vs bulk tiling")
+
+
+_KERNEL_SET_REFS = {}
+
+
+@pytest.mark.parametrize("n,mask", [(512, 1), (512, 2), (512, 4), (512, 7), (1024, 0), (1024, 1), (1024, 2), (1024, 4),
+                                    (1024, 7), (2048, 3), (2048, 4), (2048, 7)])
+def test_both_kernel_sets_vs_oracle(wso, n, mask):
+    """The warp-per-line kernels (wso_kernels2.cu: radix-32 register stages, shuffle exchanges, bulk-copy line pipeline)
+    against the oracle, alone and mixed kernel by kernel with the CTA-per-line set (mask bit k = kernel k on the
+    warp-per-line set; the two sets share the intermediate W layout).  Several frames per launch so that the persistent
+    K2 / K2h walk more than one row item per group and more than one item per launch."""
+    from watersurfacerendering_b200 import _lib
+    nframes = 7 if n <= 1024 else 3
+    times = np.array([0.75 + 0.35 * i for i in range(nframes)], np.float32)
+    if n not in _KERNEL_SET_REFS:  # the oracle frames are the slow part: once per size
+        p, o, xi = _oracle_for(n)
+        _KERNEL_SET_REFS[n] = (p, xi, {i: o.compute_waves(float(times[i])) for i in (0, nframes // 2, nframes - 1)})
+    p, xi, refs = _KERNEL_SET_REFS[n]
+    L = _lib.load()
+    assert L.wso_select_kernels(mask) == 0
+    try:
+        with wso.WSTessendorf(n, p.tile_length, max_slots=nframes) as ws:
+            ws.PrepareWithGauss(xi)
+            ws.compute_batch(times)
+            a, mn, mx = ws.read_heights(0, nframes)
+            for i in (0, nframes // 2, nframes - 1):
+                a_ref, d_ref, n_ref = refs[i]
+                assert_maps_close(ws.copy_map(0, i), ws.copy_map(1, i), d_ref, n_ref, f"N={n} mask {mask} frame {i}")
+                assert abs(a[i] - a_ref) <= SCALAR_REL_TOL * a_ref
+                assert a[i] == max(abs(mn[i]), abs(mx[i]))
+    finally:
+        L.wso_select_kernels(-1)
+
+
+def test_maps_hold_reference_defaults_before_first_compute(wso):
+    """reference: Prepare() resizes the maps with displacement (0,0,0,0) and normal (0,1,0,0) (WSTessendorf.cpp:48-54);
+    a consumer that reads them before the first ComputeWaves() must see exactly that."""
+    n = 64
+    p, o, xi = _oracle_for(n)
+    with wso.WSTessendorf(n, p.tile_length, max_slots=3) as ws:
+        ws.PrepareWithGauss(xi)
+        for slot in range(3):
+            d, nm = ws.copy_map(0, slot), ws.copy_map(1, slot)
+            assert np.all(d == 0.0)
+            assert np.all(nm[..., 1] == 1.0) and np.all(nm[..., [0, 2, 3]] == 0.0)
+        d, nm = ws.GetDisplacements(), ws.GetNormals()
+        assert np.all(d == 0.0) and np.all(nm[..., 1] == 1.0) and np.all(nm[..., [0, 2, 3]] == 0.0)
 
 
 def test_independent_tiles_in_one_batch(wso):

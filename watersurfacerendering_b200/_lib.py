@@ -80,6 +80,9 @@ SYMBOLS = {
     "wso_set_stream": (_int, [_vp, _vp]),
     "wso_alloc_host": (_int, [C.c_size_t, C.POINTER(_vp)]),
     "wso_free_host": (_int, [_vp]),
+    "wso_select_kernels": (_int, [_int]),
+    "wso_register_host": (_int, [_vp, C.c_size_t]),
+    "wso_unregister_host": (_int, [_vp]),
     "wso_get_stats": (_int, [_vp, C.POINTER(C.c_uint64), C.POINTER(_u32)]),
     "wso_set_profiling": (_int, [_vp, _int]),
     "wso_get_profile": (_int, [_vp, _vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),

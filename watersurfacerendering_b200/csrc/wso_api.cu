@@ -46,6 +46,9 @@ struct wso_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t copy_stream = nullptr;
     cudaStream_t aux_stream = nullptr;  // second compute lane: odd chunks of a batch (fills the tails of the even ones)
+    cudaStream_t more_lanes[2] = {nullptr, nullptr};  // third / fourth compute lane of wso_compute_batch (WSO_LANES)
+    cudaEvent_t ev_lane_join[2] = {nullptr, nullptr};
+    int lanes = 2;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaStream_t stream = nullptr;  // the one kernels run on (own_stream unless wso_set_stream)
     cudaEvent_t ev_chunk[2] = {nullptr, nullptr};
@@ -251,6 +254,24 @@ void free_device_buffers(wso_ctx* c) {
     cudaFreeHost(c->h_small); c->h_small = nullptr;
 }
 
+// Map contents before the first ComputeWaves(): the reference's resize() defaults (WSTessendorf.cpp:48-54) -
+// displacement (0,0,0,0), normal (0,1,0,0) - in every device slot and in the pinned host mirrors of slot 0.
+int reset_map_contents(wso_ctx* c, size_t n2, int which_mask = 3) {
+    if (which_mask & 1) {
+        WSO_CUDA(c, cudaMemsetAsync(c->d_disp, 0, sizeof(float4) * n2 * c->max_slots, c->stream));
+        if (c->h_disp) std::memset(c->h_disp, 0, sizeof(float4) * n2);
+    }
+    if ((which_mask & 2) && c->h_norm) {
+        const float4 up = make_float4(0.0f, 1.0f, 0.0f, 0.0f);
+        for (size_t i = 0; i < n2; ++i) c->h_norm[i] = up;
+        for (uint32_t sl = 0; sl < c->max_slots; ++sl)
+            WSO_CUDA(c, cudaMemcpyAsync(c->d_norm + n2 * sl, c->h_norm, sizeof(float4) * n2, cudaMemcpyHostToDevice, c->stream));
+    }
+    return WSO_OK;
+}
+
+int allocate_buffers(wso_ctx* c, uint32_t n, int logn);
+
 // (Re)allocate everything that depends on the tile size.
 int allocate_for_size(wso_ctx* c, uint32_t n) {
     int logn = 0;
@@ -258,9 +279,29 @@ int allocate_for_size(wso_ctx* c, uint32_t n) {
     WSO_CUDA(c, cudaSetDevice(c->device));
     WSO_CUDA(c, cudaStreamSynchronize(c->stream));
     free_device_buffers(c);
+    // Nothing is resident from here on: should any allocation below fail, the context stays in the "no tile prepared,
+    // no size" state (compute calls answer WSO_ERR_NOT_PREPARED, the map accessors report zero texels) instead of
+    // pointing kernels at freed buffers.
+    c->n = 0;
+    c->logn = 0;
+    c->first_use = true;
+    for (uint32_t t = 0; t < c->max_tiles; ++t) {
+        c->tiles[t].is_prepared = false;
+        c->tiles[t].h0.clear();
+    }
+    c->h_tiles.assign(c->max_tiles, TileDev{});
+    const int rc_alloc = allocate_buffers(c, n, logn);
+    if (rc_alloc != WSO_OK) {
+        free_device_buffers(c);
+        return rc_alloc;
+    }
     c->n = n;
     c->logn = logn;
-    c->first_use = true;
+    return WSO_OK;
+}
+
+int allocate_buffers(wso_ctx* c, uint32_t n, int logn) {
+    (void)logn;
     const size_t n2 = (size_t)n * n;
     // chunk: tile-frames per launch.  Keep the W scratch of one chunk around 64 MB so it stays in the
     // 126 MB L2 between K1 and K2 (16/32/48/64/96 MB measured on B200, profiles/r1j_sweep.txt:
@@ -280,7 +321,7 @@ int allocate_for_size(wso_ctx* c, uint32_t n) {
     WSO_CUDA(c, cudaMalloc(&c->d_hs, sizeof(float4) * (n2 / 2) * c->max_tiles));
     WSO_CUDA(c, cudaMalloc(&c->d_kv, sizeof(float) * n * c->max_tiles));
     WSO_CUDA(c, cudaMalloc(&c->d_tw, sizeof(float2) * n));
-    WSO_CUDA(c, cudaMalloc(&c->d_W, w_item * chunk * 2));
+    WSO_CUDA(c, cudaMalloc(&c->d_W, w_item * chunk * (size_t)(c->lanes > 2 ? c->lanes : 2)));
     for (int which = 0; which < 2; ++which) {
         const int rc = alloc_map(c, which, sizeof(float4) * n2 * c->max_slots);
         if (rc != WSO_OK) return rc;
@@ -291,9 +332,10 @@ int allocate_for_size(wso_ctx* c, uint32_t n) {
     WSO_CUDA(c, cudaMallocHost(&c->h_norm, sizeof(float4) * n2));
     c->small_cap = c->max_slots;
     WSO_CUDA(c, cudaMallocHost(&c->h_small, sizeof(float) * 3 * c->small_cap));
-    // initial map contents as the reference's resize() defaults (WSTessendorf.cpp:50-54)
-    WSO_CUDA(c, cudaMemsetAsync(c->d_disp, 0, sizeof(float4) * n2 * c->max_slots, c->stream));
-    WSO_CUDA(c, cudaMemsetAsync(c->d_norm, 0, sizeof(float4) * n2 * c->max_slots, c->stream));
+    {
+        const int rc = reset_map_contents(c, n2);
+        if (rc != WSO_OK) return rc;
+    }
     // twiddles exp(+2 pi i k / N), computed in float64
     std::vector<float2> tw(n);
     for (uint32_t k = 0; k < n; ++k) {
@@ -301,7 +343,6 @@ int allocate_for_size(wso_ctx* c, uint32_t n) {
         tw[k] = make_float2((float)std::cos(a), (float)std::sin(a));
     }
     WSO_CUDA(c, cudaMemcpyAsync(c->d_tw, tw.data(), sizeof(float2) * n, cudaMemcpyHostToDevice, c->stream));
-    c->h_tiles.assign(c->max_tiles, TileDev{});
     for (uint32_t t = 0; t < c->max_tiles; ++t) {
         c->h_tiles[t].h0 = c->d_h0 + n2 * t;
         c->h_tiles[t].hs = c->d_hs + (n2 / 2) * t;
@@ -546,6 +587,15 @@ int wso_create(const wso_params* p, int device, uint32_t max_tiles, uint32_t max
         if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess) { rc = fail_cuda(nullptr, e, "cudaStreamCreate"); break; }
         if ((e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) { rc = fail_cuda(nullptr, e, "cudaStreamCreate"); break; }
         if ((e = cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking)) != cudaSuccess) { rc = fail_cuda(nullptr, e, "cudaStreamCreate"); break; }
+        if (const char* env = std::getenv("WSO_LANES")) {  // compute lanes of a batched call (default 2)
+            const int v = std::atoi(env);
+            if (v >= 1 && v <= 4) c->lanes = v;
+        }
+        for (int i = 0; i < 2 && rc == WSO_OK; ++i) {
+            if ((e = cudaStreamCreateWithFlags(&c->more_lanes[i], cudaStreamNonBlocking)) != cudaSuccess) rc = fail_cuda(nullptr, e, "cudaStreamCreate");
+            else if ((e = cudaEventCreateWithFlags(&c->ev_lane_join[i], cudaEventDisableTiming)) != cudaSuccess) rc = fail_cuda(nullptr, e, "cudaEventCreate");
+        }
+        if (rc != WSO_OK) break;
         if ((e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming)) != cudaSuccess) { rc = fail_cuda(nullptr, e, "cudaEventCreate"); break; }
         if ((e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming)) != cudaSuccess) { rc = fail_cuda(nullptr, e, "cudaEventCreate"); break; }
         for (int i = 0; i < 2; ++i) {
@@ -577,6 +627,13 @@ int wso_destroy(wso_ctx* c) {
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+    for (int i = 0; i < 2; ++i) {
+        if (c->more_lanes[i]) {
+            cudaStreamSynchronize(c->more_lanes[i]);
+            cudaStreamDestroy(c->more_lanes[i]);
+        }
+        if (c->ev_lane_join[i]) cudaEventDestroy(c->ev_lane_join[i]);
+    }
     for (int i = 0; i < 2; ++i) {
         if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]);
         if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
@@ -706,22 +763,25 @@ int wso_compute_batch(wso_ctx* c, uint32_t n, const uint32_t* tiles, const float
     // Two compute lanes: even chunks on the caller-visible stream, odd chunks on an internal one, each lane with
     // its own W scratch.  Chunks are independent, so the second lane's kernels fill the partial last wave and the
     // launch gaps of the first.  Fork/join events keep everything ordered with respect to c->stream.
-    const bool two_lanes = n > c->chunk && !c->profiling;  // per-kernel event timing wants the kernels serialised
-    if (two_lanes) {
+    const uint32_t n_chunks = (n + c->chunk - 1) / c->chunk;
+    // per-kernel event timing wants the kernels serialised
+    const int lanes = c->profiling ? 1 : (int)(n_chunks < (uint32_t)c->lanes ? n_chunks : (uint32_t)c->lanes);
+    auto lane_stream = [&](int l) { return l == 0 ? c->stream : (l == 1 ? c->aux_stream : c->more_lanes[l - 2]); };
+    if (lanes > 1) {
         WSO_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));
-        WSO_CUDA(c, cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
+        for (int l = 1; l < lanes; ++l) WSO_CUDA(c, cudaStreamWaitEvent(lane_stream(l), c->ev_fork, 0));
     }
     int lane = 0;
     for (uint32_t done = 0; done < n; done += c->chunk) {
         const uint32_t m = (n - done < c->chunk) ? (n - done) : c->chunk;
-        rc = enqueue_chunk(c, m, tiles ? tiles + done : nullptr, t + done, first_slot + done, lane,
-                           lane ? c->aux_stream : c->stream);
+        rc = enqueue_chunk(c, m, tiles ? tiles + done : nullptr, t + done, first_slot + done, lane, lane_stream(lane));
         if (rc != WSO_OK) return rc;
-        if (two_lanes) lane ^= 1;
+        lane = (lane + 1 == lanes) ? 0 : lane + 1;
     }
-    if (two_lanes) {
-        WSO_CUDA(c, cudaEventRecord(c->ev_join, c->aux_stream));
-        WSO_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    for (int l = 1; l < lanes; ++l) {
+        cudaEvent_t ev = l == 1 ? c->ev_join : c->ev_lane_join[l - 2];
+        WSO_CUDA(c, cudaEventRecord(ev, lane_stream(l)));
+        WSO_CUDA(c, cudaStreamWaitEvent(c->stream, ev, 0));
     }
     return WSO_OK;
 }
@@ -881,8 +941,9 @@ int wso_set_exportable(wso_ctx* c, int on) {
                 if (map_ptr(c, w) == nullptr) alloc_map(c, w, bytes);
             return fail(c, rc, msg);
         }
-        WSO_CUDA(c, cudaMemsetAsync(map_ptr(c, which), 0, bytes, c->stream));
     }
+    rc = reset_map_contents(c, (size_t)c->n * c->n);
+    if (rc != WSO_OK) return rc;
     WSO_CUDA(c, cudaStreamSynchronize(c->stream));
     return WSO_OK;
 }
@@ -935,7 +996,10 @@ int wso_import_external_fd(wso_ctx* c, int which, int fd, size_t bytes, size_t o
     map_ptr(c, which) = static_cast<float4*>(ptr);
     c->map_mem[which].kind = kBackExternal;
     c->map_mem[which].ext = ext;
-    WSO_CUDA(c, cudaMemsetAsync(ptr, 0, need, c->stream));
+    {
+        const int rc = reset_map_contents(c, (size_t)c->n * c->n, which == WSO_MAP_DISPLACEMENT ? 1 : 2);
+        if (rc != WSO_OK) return rc;
+    }
     WSO_CUDA(c, cudaStreamSynchronize(c->stream));
     return WSO_OK;
 }
@@ -992,6 +1056,32 @@ int wso_alloc_host(size_t bytes, void** ptr) {
     if (!ptr) return WSO_ERR_INVALID_ARG;
     cudaError_t e = cudaMallocHost(ptr, bytes);
     if (e != cudaSuccess) return fail_cuda(nullptr, e, "cudaMallocHost");
+    return WSO_OK;
+}
+
+int wso_select_kernels(int mask) {
+    if (mask < -1 || mask > 7) return WSO_ERR_INVALID_ARG;
+    wso::set_warp_core_override(mask);
+    return WSO_OK;
+}
+
+int wso_register_host(void* ptr, size_t bytes) {
+    if (!ptr || bytes == 0) return WSO_ERR_INVALID_ARG;
+    const cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return e == cudaErrorMemoryAllocation ? WSO_ERR_OUT_OF_MEMORY : WSO_ERR_CUDA;
+    }
+    return WSO_OK;
+}
+
+int wso_unregister_host(void* ptr) {
+    if (!ptr) return WSO_ERR_INVALID_ARG;
+    const cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return WSO_ERR_CUDA;
+    }
     return WSO_OK;
 }
 

@@ -1,6 +1,7 @@
 // wso_kernels.cu — __global__ entry points and launch dispatch for sm_100a.
 #include "wso_launch.h"
 
+#include <atomic>
 #include <cstdlib>
 #include <type_traits>
 
@@ -140,14 +141,22 @@ static cudaError_t launch_pdl(Kern kern, dim3 grid, int threads, int smem, cudaS
     return cudaLaunchKernelEx(&cfg, kern, args);
 }
 
-// Which of K1 / K2h / K2 run on the warp-per-line kernels when a launch qualifies: all three unless WSO_WARP_CORE says
-// otherwise (a bit mask, 0 = the CTA-per-line kernels of this file; used for A/B measurements).
-static int warp_core_mask() {
-    static const int mask = [] {
+// Which of K1 / K2h / K2 (bits 0 / 1 / 2) of a qualifying batched launch run on the warp-per-line kernels of
+// wso_kernels2.cu.  Default = what measured faster on B200 (profiles/r2_ab_kernel_sets.md): the height pre-pass K2h at
+// 1024^2; everything else stays on the CTA-per-line kernels of this file.  WSO_WARP_CORE overrides the mask for every
+// supported size (0 = none, 7 = all three) - used by the A/B measurements and the parity tests of both kernel sets.
+static std::atomic<int> g_warp_core_override{-1};  // wso_select_kernels(): -1 = no override
+void set_warp_core_override(int mask) { g_warp_core_override.store(mask < 0 ? -1 : (mask & 7), std::memory_order_relaxed); }
+
+static int warp_core_mask(int logn) {
+    static const int env_mask = [] {
         const char* env = std::getenv("WSO_WARP_CORE");
-        return env ? (std::atoi(env) & 7) : 0;
+        return env ? (std::atoi(env) & 7) : -1;
     }();
-    return mask;
+    const int forced = g_warp_core_override.load(std::memory_order_relaxed);
+    if (forced >= 0) return forced & 7;
+    if (env_mask >= 0) return env_mask;
+    return logn == 10 ? 2 : 0;
 }
 
 // Jacobian mode: K1 (general body, field 1 with its real slot filled), K2h, K2 with four lines per CTA
@@ -159,18 +168,19 @@ static cudaError_t launch_tiled_jacobian(const Args& args, int n_items, cudaStre
         using P1 = Pass1<LOGN, TL::CP, TL::NF>;
         using PJ = Pass2<LOGN, 1, false, false, false, true>;
         using PH = Pass2<LOGN, TL::RH, true>;
-        static bool configured[16] = {};  // per device: opt in to > 48 KB of dynamic shared memory once
+        static std::atomic<bool> configured[16];  // per device: opt in to > 48 KB of dynamic shared memory once
         int dev = 0;
         cudaGetDevice(&dev);
         cudaError_t e;
-        if (dev < 0 || dev >= 16 || !configured[dev]) {
+        if (dev < 0 || dev >= 16 || !configured[dev].load(std::memory_order_acquire)) {
             e = cudaFuncSetAttribute(wso_pass1_kernel<LOGN, TL, Args, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P1::SMEM_BYTES);
             if (e != cudaSuccess) return e;
             e = cudaFuncSetAttribute(wso_pass2j_kernel<LOGN, Args>, cudaFuncAttributeMaxDynamicSharedMemorySize, PJ::SMEM_BYTES);
             if (e != cudaSuccess) return e;
             e = cudaFuncSetAttribute(wso_heights_kernel<LOGN, TL, Args>, cudaFuncAttributeMaxDynamicSharedMemorySize, PH::SMEM_BYTES);
             if (e != cudaSuccess) return e;
-            if (dev >= 0 && dev < 16) configured[dev] = true;
+            // (the attribute calls are idempotent: two threads racing here both complete them before either publishes)
+            if (dev >= 0 && dev < 16) configured[dev].store(true, std::memory_order_release);
         }
         if (ev) cudaEventRecord(ev[0], stream);
         e = launch_pdl(wso_pass1_kernel<LOGN, TL, Args, false, true>, dim3(P1::H / TL::CP, 4 / TL::NF, n_items), P1::T,
@@ -192,10 +202,10 @@ static cudaError_t launch_tiled(const Args& args, int n_items, cudaStream_t stre
     using P1 = Pass1<LOGN, TL::CP, TL::NF>;
     using P2 = Pass2<LOGN, TL::RI, false>;
     using PH = Pass2<LOGN, TL::RH, true>;
-    static bool configured[16] = {};  // per device: opt in to > 48 KB of dynamic shared memory once
+    static std::atomic<bool> configured[16];  // per device: opt in to > 48 KB of dynamic shared memory once
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 16 || !configured[dev]) {
+    if (dev < 0 || dev >= 16 || !configured[dev].load(std::memory_order_acquire)) {
         cudaError_t e;
         e = cudaFuncSetAttribute(wso_pass1_kernel<LOGN, TL, Args, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P1::SMEM_BYTES);
         if (e != cudaSuccess) return e;
@@ -205,7 +215,7 @@ static cudaError_t launch_tiled(const Args& args, int n_items, cudaStream_t stre
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(wso_heights_kernel<LOGN, TL, Args>, cudaFuncAttributeMaxDynamicSharedMemorySize, PH::SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        if (dev >= 0 && dev < 16) configured[dev] = true;
+        if (dev >= 0 && dev < 16) configured[dev].store(true, std::memory_order_release);
     }
     cudaError_t e;
     if (ev) cudaEventRecord(ev[0], stream);
@@ -219,7 +229,7 @@ static cudaError_t launch_tiled(const Args& args, int n_items, cudaStream_t stre
     // batched launches of 512^2 / 1024^2 / 2048^2 run on the warp-per-line kernels (wso_kernels2.cu); mask bit k = kernel k
     int warp_mask = 0;
     if constexpr (std::is_same<Args, LaunchArgs>::value) {
-        if (fast && warp_core_supported(LOGN)) warp_mask = warp_core_mask();
+        if (fast && warp_core_supported(LOGN)) warp_mask = warp_core_mask(LOGN);
     }
     if constexpr (std::is_same<Args, LaunchArgs>::value) {
         if (warp_mask & 1) e = launch_warp_core(LOGN, 0, args, n_items, stream);

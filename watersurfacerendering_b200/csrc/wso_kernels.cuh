@@ -1044,10 +1044,13 @@ struct Pass2 {
     static WSO_HD void pack(Exec& ex, const float2* smem, const float2* smem_peer, int bx, int by, int bz, int crank,
                             const Args& args) {
         const BatchItem item = args.items[bz];
-        ex.pdl_wait();
+        // Only the displacement map needs K2h's result (disp.y is written already divided by A): the CTAs of the normal
+        // map pack right away and fill the device while K2h drains.
+        const bool needs_amp = JAC || by == 0;
+        if (needs_amp) ex.pdl_wait();
         ex.pdl_release();
         const float lambda = args.td[bz].lambda;
-        const float amp = amplitude_of(args.minmax[2 * item.slot], args.minmax[2 * item.slot + 1]);
+        const float amp = needs_amp ? amplitude_of(args.minmax[2 * item.slot], args.minmax[2 * item.slot + 1]) : 1.0f;
         const float inv_amp = rdiv(1.0f, amp);
         if (bx == 0 && by == 0 && crank == 0) {
             ex.each([&](int tid, ThreadState&) {

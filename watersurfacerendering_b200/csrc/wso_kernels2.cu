@@ -7,9 +7,9 @@
 
 namespace wso {
 
-// Tiling per tile size.  CP column pairs x NF packed fields per K1 CTA (CP*L threads); GPC line groups (L threads each)
-// per K2 / K2h CTA.  All CTAs are 128 threads: 3-4 of them share an SM and drift apart in phase (record loads, register
-// stages, map stores), which is what keeps the memory pipes busy without CTA-wide barriers.
+// Tiling per tile size.  K1: CP column pairs x NF packed fields per CTA, one line group of L = N/32 threads per
+// (column pair, field) -> CP*NF*L threads; K2 / K2h: GPC line groups per CTA.  The register budget (and with it the
+// number of resident warps) follows from the CTA size: K1 runs 512-thread CTAs at <= 128 registers (16 warps per SM).
 #ifndef WSO_V2_CP9
 #define WSO_V2_CP9 8
 #define WSO_V2_GPC9 8
@@ -25,19 +25,29 @@ namespace wso {
 #ifndef WSO_V2_NF
 #define WSO_V2_NF 4
 #endif
-#ifndef WSO_V2_MINB1
-#define WSO_V2_MINB1 3
+#ifndef WSO_V2_REGS1
+#define WSO_V2_REGS1 128  // register budget per K1 thread
 #endif
 #ifndef WSO_V2_MINB2
 #define WSO_V2_MINB2 3
 #endif
+#ifndef WSO_V2_REGSH
+#define WSO_V2_REGSH 128  // register budget per K2h thread (no pack phase: one transformed line and the twiddles)
+#endif
+#ifndef WSO_V2_NBUFH
+#define WSO_V2_NBUFH 1
+#endif
+constexpr int min_blocks_for(int threads, int regs) {
+    return (65536 / regs) / threads < 1 ? 1 : (65536 / regs) / threads;
+}
 template <int LOGN> struct Cfg2;
 template <> struct Cfg2<9>  { static constexpr int CP = WSO_V2_CP9,  NF = WSO_V2_NF, GPC = WSO_V2_GPC9; };
 template <> struct Cfg2<10> { static constexpr int CP = WSO_V2_CP10, NF = WSO_V2_NF, GPC = WSO_V2_GPC10; };
 template <> struct Cfg2<11> { static constexpr int CP = WSO_V2_CP11, NF = WSO_V2_NF, GPC = WSO_V2_GPC11; };
 
 template <int LOGN, class Args>
-__global__ void __launch_bounds__(v2::Pass1W<LOGN, Cfg2<LOGN>::CP, Cfg2<LOGN>::NF>::T, WSO_V2_MINB1)
+__global__ void __launch_bounds__(v2::Pass1W<LOGN, Cfg2<LOGN>::CP, Cfg2<LOGN>::NF>::T,
+                                   min_blocks_for(v2::Pass1W<LOGN, Cfg2<LOGN>::CP, Cfg2<LOGN>::NF>::T, WSO_V2_REGS1))
 wso_pass1w_kernel(const __grid_constant__ Args args) {
     extern __shared__ __align__(128) float2 smem[];
     DevCtx cx;
@@ -55,12 +65,15 @@ wso_pass2w_kernel(const __grid_constant__ Args args, int n_items) {
     else P2::template run<1>(cx, smem, blockIdx.x, gridDim.x, n_items, args);
 }
 
+template <int LOGN>
+using PassH = v2::Pass2W<LOGN, Cfg2<LOGN>::GPC, WSO_V2_NBUFH>;
+
 template <int LOGN, class Args>
-__global__ void __launch_bounds__(v2::Pass2W<LOGN, Cfg2<LOGN>::GPC>::T, WSO_V2_MINB2)
+__global__ void __launch_bounds__(PassH<LOGN>::T, min_blocks_for(PassH<LOGN>::T, WSO_V2_REGSH))
 wso_heightsw_kernel(const __grid_constant__ Args args, int n_items) {
     extern __shared__ __align__(128) float2 smem[];
     DevCtx cx;
-    v2::Pass2W<LOGN, Cfg2<LOGN>::GPC>::template run<2>(cx, smem, blockIdx.x, gridDim.x, n_items, args);
+    PassH<LOGN>::template run<2>(cx, smem, blockIdx.x, gridDim.x, n_items, args);
 }
 
 namespace {
@@ -106,11 +119,11 @@ const DevPlan& plan_for_device() {
     auto kh = wso_heightsw_kernel<LOGN, LaunchArgs>;
     cudaError_t e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, P1::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, P2::SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(kh, cudaFuncAttributeMaxDynamicSharedMemorySize, P2::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kh, cudaFuncAttributeMaxDynamicSharedMemorySize, PassH<LOGN>::SMEM_BYTES);
     int sms = 0, occ2 = 0, occh = 0;
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k2, P2::T, P2::SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occh, kh, P2::T, P2::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occh, kh, PassH<LOGN>::T, PassH<LOGN>::SMEM_BYTES);
     if (e == cudaSuccess && (occ2 < 1 || occh < 1)) e = cudaErrorLaunchOutOfResources;
     p.err = e;
     if (const char* env = std::getenv("WSO_V2_OCC")) {  // tuning: cap the resident CTAs per SM of the persistent kernels
@@ -138,11 +151,11 @@ template <int LOGN>
 cudaError_t launch_k2h(const LaunchArgs& args, int n_items, cudaStream_t stream) {
     const DevPlan& p = plan_for_device<LOGN>();
     if (p.err != cudaSuccess) return p.err;
-    using P2 = v2::Pass2W<LOGN, Cfg2<LOGN>::GPC>;
-    const int units = n_items * P2::H;
+    using PH = PassH<LOGN>;
+    const int units = n_items * PH::H;
     int ctas = (units + Cfg2<LOGN>::GPC - 1) / Cfg2<LOGN>::GPC;
     if (ctas > p.ctas_k2h) ctas = p.ctas_k2h;
-    return launch_pdl2(wso_heightsw_kernel<LOGN, LaunchArgs>, dim3(ctas, 1, 1), P2::T, P2::SMEM_BYTES, stream, args, n_items);
+    return launch_pdl2(wso_heightsw_kernel<LOGN, LaunchArgs>, dim3(ctas, 1, 1), PH::T, PH::SMEM_BYTES, stream, args, n_items);
 }
 template <int LOGN>
 cudaError_t launch_k2(const LaunchArgs& args, int n_items, cudaStream_t stream) {
@@ -150,7 +163,8 @@ cudaError_t launch_k2(const LaunchArgs& args, int n_items, cudaStream_t stream) 
     if (p.err != cudaSuccess) return p.err;
     using P2 = v2::Pass2W<LOGN, Cfg2<LOGN>::GPC>;
     const int units = n_items * P2::H;
-    int ctas = (units + Cfg2<LOGN>::GPC - 1) / Cfg2<LOGN>::GPC;
+    constexpr int upc = Cfg2<LOGN>::GPC / 2;  // a row item of a map occupies two line groups
+    int ctas = (units + upc - 1) / upc;
     if (ctas > p.ctas_k2 / 2) ctas = p.ctas_k2 / 2;  // the two maps share the device
     if (ctas < 1) ctas = 1;
     return launch_pdl2(wso_pass2w_kernel<LOGN, LaunchArgs>, dim3(ctas, 2, 1), P2::T, P2::SMEM_BYTES, stream, args, n_items);

@@ -26,6 +26,8 @@ int kernels_per_launch();
 // records, no Jacobian channel.  which: 0 = K1, 1 = K2h, 2 = K2 (same W layout and stream protocol as the kernels of
 // wso_kernels.cu, so the two sets can be mixed kernel by kernel).
 bool warp_core_supported(int logn);
+// process-wide override of the kernel-set choice (bit k = kernel k on the warp-per-line set; -1 = built-in default)
+void set_warp_core_override(int mask);
 cudaError_t launch_warp_core(int logn, int which, const LaunchArgs& args, int n_items, cudaStream_t stream);
 
 // Slab-decomposed path (one grid over several devices).  phase 0: K1 on this device's column pairs,
