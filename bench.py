@@ -45,8 +45,9 @@ WORKLOADS = {
                desc="BASELINE configs[1]: 1024x1024 tile animated, t_i = i*0.05 s, 100 frames per step"),
     "c3": dict(n=2048, L=4000.0, seed=2, frames=32, tiles=1, dt=0.05,
                desc="BASELINE configs[2]: 2048x2048 tile, all maps, frames t_i = i*0.05 s, 32 frames per step per GPU"),
-    "c4": dict(n=512, L=1000.0, seed=1000, frames=64, tiles=64, dt=0.0,
-               desc="BASELINE configs[3]: 64 independent 512x512 tiles (wind angle 2*pi*j/64, V=5+0.5j, seed 1000+j), t=10"),
+    "c4": dict(n=512, L=1000.0, seed=1000, frames=64, tiles=64, dt=0.05, t0=10.0, times_per_step=16,
+               desc="BASELINE configs[3]: 64 independent 512x512 tiles (wind angle 2*pi*j/64, V=5+0.5j, seed 1000+j), "
+                    "tile j on GPU j mod P, every step = all tiles at 16 consecutive times t = 10 + 0.05*k"),
     # one grid over ALL ranks (strong scaling): slab-decomposed transform with one exchange step (run_slab below)
     "c5": dict(n=16384, L=32000.0, seed=7, frames=1, tiles=1, dt=0.05, t0=10.0,
                desc="BASELINE configs[4]: single 16384x16384 patch, slab-decomposed over the ranks, t = 10 + 0.05*k"),
@@ -172,10 +173,10 @@ def tile_params(wl, j):
 
 def step_times(wl, step):
     f = wl["frames"]
+    if wl["tiles"] > 1:
+        return np.full(f, wl.get("t0", 10.0) + wl["dt"] * step, np.float32), np.arange(f, dtype=np.uint32) % wl["tiles"]
     if "t0" in wl:
         return np.array([wl["t0"] + wl["dt"] * step], np.float32), None
-    if wl["tiles"] > 1:
-        return np.full(f, 10.0, np.float32), np.arange(f, dtype=np.uint32) % wl["tiles"]
     i0 = step * f
     return (np.arange(i0, i0 + f, dtype=np.float32) * np.float32(wl["dt"])), None
 
@@ -417,6 +418,295 @@ def run_slab(args, wl, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Run this rank (and first-touch its pinned host buffers) on the CPUs next to its GPU.  Under torchrun every rank
+    otherwise starts on the same NUMA node and the end-to-end path (D2H into pinned memory) of 8 ranks funnels through one
+    memory controller / one PCIe root.  Returns the CPU list, or None when NVML cannot tell."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[gpu_index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else gpu_index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return allowed
+    except Exception:
+        pass
+    return None
+
+
+def kernel_names():
+    """Which implementation of K1 / K2h / K2 a batched launch of this size runs (wso_select_kernels / WSO_WARP_CORE)."""
+    return {"K1": "wso_pass1_kernel / wso_pass1w_kernel (evolve + first transform)",
+            "K2h": "wso_heights_kernel / wso_heightsw_kernel (height extrema)",
+            "K2": "wso_pass2_kernel / wso_pass2w_kernel (second transform + pack)"}
+
+
+def load_traffic(workload):
+    """Measured DRAM bytes per tile-frame and kernel (ncu --cache-control none, caches left alone between kernels:
+    tools/gpu_traffic.sh -> profiles/roofline_traffic.json)."""
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    try:
+        return json.load(open(tpath)).get(workload)
+    except Exception:
+        return None
+
+
+def local_plan(wl, rank, world):
+    """Tile-frames this rank processes per step: (frames F, local tile ids or None, global tile ids)."""
+    if wl["tiles"] > 1:
+        from watersurfacerendering_b200 import sharding
+        mine = sharding.shard_indices(wl["tiles"], rank, world)   # tile j -> rank j mod P (BASELINE configs[3])
+        return len(mine) * wl.get("times_per_step", 1), mine
+    return wl["frames"], None
+
+
+def local_step_times(wl, step, mine):
+    """(times, local tile index per tile-frame) of one step on this rank."""
+    if mine is not None:
+        k = wl.get("times_per_step", 1)
+        t = wl.get("t0", 10.0) + wl["dt"] * (step * k + np.arange(k, dtype=np.float32))
+        times = np.repeat(t.astype(np.float32), len(mine))
+        tiles = np.tile(np.arange(len(mine), dtype=np.uint32), k)
+        return times, tiles
+    return step_times(wl, step)
+
+
+def bench_workload(name, wl, steps, warmup, rank, world, local_rank, *, want_e2e=True, e2e_frames=0, clocks=True):
+    """One workload on this rank's GPU: device-resident throughput, per-kernel times, end-to-end through host buffers."""
+    import torch
+    import torch.distributed as dist
+    import watersurfacerendering_b200 as W
+    from watersurfacerendering_b200 import sharding
+
+    n = wl["n"]
+    F, mine = local_plan(wl, rank, world)
+    ntiles = len(mine) if mine is not None else 1
+    ws = W.WSTessendorf(n, wl["L"], device=local_rank, max_tiles=ntiles, max_slots=max(F, 2))
+    for jl in range(ntiles):
+        j = int(mine[jl]) if mine is not None else 0
+        prm = tile_params(wl, j)
+        ws.SetWindDirection(prm["wind"], jl)
+        ws.SetWindSpeed(prm["speed"], jl)
+        # every rank owns its own realisation (its tiles / its share of the animation)
+        ws.PrepareWithGauss(gauss(n, wl["seed"] + j + (7919 * rank if mine is None else 0)), tile=jl)
+    # a dedicated (non-default) torch stream carries every kernel, so torch.cuda.Event brackets them
+    stream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    ws.set_stream(stream.cuda_stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run_steps(first, count):
+        for k in range(first, first + count):
+            t, tl = local_step_times(wl, k, mine)
+            ws.compute_batch(t, tiles=tl, first_slot=0)
+
+    def reduce_ranks(x, op):
+        if world == 1:
+            return x
+        tt = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=op)
+        return float(tt.item())
+
+    # ---- device-resident throughput -------------------------------------------------------------
+    run_steps(0, warmup)
+    barrier()
+    sampler = ClockSampler(local_rank) if clocks else None
+    if rank == 0 and sampler:
+        sampler.start()
+    l0 = ws.stats()["kernel_launches"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    run_steps(warmup, steps)
+    e1.record(stream)
+    barrier()
+    ms = reduce_ranks(e0.elapsed_time(e1), dist.ReduceOp.MAX)
+    launches = ws.stats()["kernel_launches"] - l0
+    clk = sampler.stop() if (rank == 0 and sampler) else None
+    frames_all = reduce_ranks(float(F), dist.ReduceOp.SUM)   # tile-frames per step over all ranks
+    value = frames_all * steps / (ms * 1e-3)
+
+    # ---- per-kernel timing (same steps again, CUDA events around every launch) -----------------------
+    ws.set_profiling(True)
+    run_steps(warmup, steps)
+    prof = ws.profile()
+    ws.set_profiling(False)
+    names = KERNELS
+    kms = prof["ms"]
+    dom = int(np.argmax(kms))
+    peak, peak_src = measured_peak()
+    pts = float(n) * n
+    tf = max(prof["tile_frames"], 1)
+
+    def gbs(bytes_per_pt, k):
+        return bytes_per_pt * pts * tf / (kms[k] * 1e-3) / 1e9 if kms[k] > 0 else None
+
+    traffic = load_traffic(name)
+    per_launch_tf = tf / max(prof["launches"], 1)
+    achieved = gbs(BYTES_PER_POINT[names[dom]], dom)
+    us_tf = ms * 1e3 / (F * steps)
+    roofline = {
+        "bound": "hbm", "kernel": kernel_names()[names[dom]],
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
+        "peak_source": peak_src,
+        # DRAM bytes the dominant kernel really moved per launch: ncu --cache-control none (caches left alone between
+        # kernels, i.e. what the running pipeline sees), per tile-frame x tile-frames per launch of THIS run
+        "traffic": (traffic["bytes_per_tile_frame"][names[dom]] * per_launch_tf) if traffic else None,
+        "traffic_source": (traffic or {}).get("capture"),
+        "algorithmic_bytes_per_launch": BYTES_PER_POINT[names[dom]] * pts * per_launch_tf,
+        "avg_launch_ms": kms[dom] / max(prof["launches"], 1),
+        "timing": "cudaEvent pairs around every launch on the compute stream, separate pass over the same K steps",
+        "kernel_ms": dict(zip(names, kms)),
+        "kernel_share": dict(zip(names, [x / sum(kms) for x in kms])),
+        "per_kernel_achieved_gbs": {nm: gbs(BYTES_PER_POINT[nm], i) for i, nm in enumerate(names)},
+        "survey_model_achieved_gbs": gbs(SURVEY_BYTES_PER_POINT[names[dom]], dom),
+        "whole_path_gbs": sum(BYTES_PER_POINT.values()) * pts / (us_tf * 1e-6) / 1e9,
+        "whole_path_frac_survey_model": sum(SURVEY_BYTES_PER_POINT.values()) * pts / (us_tf * 1e-6) / 1e9 / peak,
+        "whole_path_frac_design_bytes": sum(BYTES_PER_POINT.values()) * pts / (us_tf * 1e-6) / 1e9 / peak,
+        "whole_path_frac_dram_measured": (sum(traffic["bytes_per_tile_frame"].values()) / (us_tf * 1e-6) / 1e9 / peak)
+        if traffic else None,
+    }
+    out = {"value": value, "ms": ms, "us_per_tile_frame": us_tf, "launches": int(launches), "clocks": clk,
+           "roofline": roofline, "frames_per_step_local": F, "frames_per_step_all": int(frames_all),
+           "chunk": ws.stats()["chunk"], "tiles_local": ntiles}
+
+    # ---- end to end: host output buffers, D2H inside the timed region ---------------------------------
+    if want_e2e:
+        Fe = e2e_frames or min(F, 24)
+        disp = W.PinnedBuffer((Fe, n, n, 4))
+        norm = W.PinnedBuffer((Fe, n, n, 4))
+
+        def e2e_step(k):
+            t, tl = local_step_times(wl, k, mine)
+            a, mn, mx = ws.compute_to_host(t[:Fe], disp.array, norm.array, tiles=None if tl is None else tl[:Fe])
+            return a
+
+        for k in range(warmup):
+            e2e_step(k)
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(warmup, warmup + steps):
+            amps = e2e_step(k)
+        torch.cuda.synchronize()
+        e2e_s = reduce_ranks(time.perf_counter() - t0, dist.ReduceOp.MAX)
+        barrier()
+        fe_all = reduce_ranks(float(Fe), dist.ReduceOp.SUM)
+        e2e_val = fe_all * steps / e2e_s
+        d2h = int(2 * 16 * n * n * Fe + 12 * Fe)
+        # the host-side ceiling of that number: the same two map copies per step, device -> the same pinned buffers,
+        # with no kernels at all (PCIe / host memory system only)
+        dev = torch.empty(2 * 16 * n * n * Fe, dtype=torch.uint8, device="cuda")
+        hd = torch.from_numpy(disp.array.view(np.uint8).reshape(-1))
+        hn = torch.from_numpy(norm.array.view(np.uint8).reshape(-1))
+        half = dev.numel() // 2
+        for _ in range(2):
+            hd.copy_(dev[:half], non_blocking=True)
+            hn.copy_(dev[half:], non_blocking=True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            hd.copy_(dev[:half], non_blocking=True)
+            hn.copy_(dev[half:], non_blocking=True)
+        torch.cuda.synchronize()
+        probe_s = reduce_ranks(time.perf_counter() - t0, dist.ReduceOp.MAX)
+        barrier()
+        pcie_gbs = dev.numel() * steps / probe_s / 1e9               # this rank's copies over its own link
+        pcie_tfs = fe_all * steps / probe_s                          # tile-frames/s if only the copies existed
+        del dev
+        all_amps = sharding.gather_in_global_order(amps.tolist(), int(fe_all), rank, world) if (world > 1 and mine is None) else amps
+        out["e2e"] = {"value": e2e_val, "unit": "tile-frames/s", "h2d_bytes_per_step": int(4 * Fe),
+                      "d2h_bytes_per_step": d2h, "frames_per_step_per_gpu": Fe,
+                      "api": "wso_compute_to_host (C ABI), pinned host maps, copies overlapped with the next chunk",
+                      "last_amplitude": float(np.asarray(all_amps)[-1]),
+                      "d2h_probe": {"what": "the same D2H copies with no kernels (host-side ceiling, max over ranks)",
+                                    "gbs_per_gpu": pcie_gbs, "tile_frames_per_s": pcie_tfs,
+                                    "e2e_frac_of_probe": e2e_val / pcie_tfs}}
+        # zero-host-copy variant (SURVEY row f-2): the maps live in exportable memory a Vulkan device imports with
+        # VK_KHR_external_memory_fd; the consumer reads them where K2 wrote them, so the end-to-end cost is the device
+        # path itself plus the semaphore signal.  Timed with the exportable backing in place.
+        try:
+            ws.set_exportable(True)
+            run_steps(0, 1)
+            barrier()
+            e0.record(stream)
+            run_steps(warmup, steps)
+            e1.record(stream)
+            barrier()
+            ms_x = reduce_ranks(e0.elapsed_time(e1), dist.ReduceOp.MAX)
+            out["e2e"]["zero_copy_export"] = {"value": frames_all * steps / (ms_x * 1e-3), "unit": "tile-frames/s",
+                                              "what": "maps in exportable (POSIX fd) device memory, no host copy"}
+        except Exception as ex:  # no virtual-memory API on this driver: report, do not fail the bench
+            out["e2e"]["zero_copy_export"] = {"unavailable": repr(ex)[:200]}
+        disp.close()
+        norm.close()
+    ws.close()
+    torch.cuda.synchronize()
+    return out
+
+
+def c1_latency(local_rank):
+    """North-star target 'a 512^2 tile (all maps) in <= 20 us': one ComputeWaves-sized call at a time.
+    isolated: CUDA events around ONE tile-frame, median; back to back: per frame of a stream of single-frame calls
+    (a) through the Python binding, (b) through the C ABI with no Python in the loop (tools/lat_bench, when it builds)."""
+    import torch
+    import watersurfacerendering_b200 as W
+    wl = WORKLOADS["c1"]
+    n = wl["n"]
+    ws = W.WSTessendorf(n, wl["L"], device=local_rank, max_tiles=1, max_slots=4)
+    ws.PrepareWithGauss(gauss(n, wl["seed"]))
+    stream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(stream)
+    ws.set_stream(stream.cuda_stream)
+    t = np.zeros(1, np.float32)
+    for i in range(50):
+        t[0] = 0.05 * i
+        ws.compute_batch(t)
+    torch.cuda.synchronize()
+    iso = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for i in range(200):
+        t[0] = 3.0 + 0.05 * i
+        e0.record(stream)
+        ws.compute_batch(t)
+        e1.record(stream)
+        e1.synchronize()
+        iso.append(e0.elapsed_time(e1) * 1e3)
+    frames = 2000
+    e0.record(stream)
+    c0 = time.perf_counter()
+    for i in range(frames):
+        t[0] = 20.0 + 0.05 * i
+        ws.compute_batch(t, first_slot=i & 3)
+    c1 = time.perf_counter()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    out = {"isolated_us_median": float(np.median(iso)), "isolated_us_min": float(np.min(iso)),
+           "back_to_back_us_python_binding": e0.elapsed_time(e1) * 1e3 / frames,
+           "host_enqueue_us_python_binding": (c1 - c0) * 1e6 / frames}
+    ws.close()
+    exe = os.path.join(ROOT, "tools", "lat_bench")
+    try:
+        if not os.path.exists(exe):
+            subprocess.run(["make", "-C", os.path.join(ROOT, "examples"), "lat_bench"], capture_output=True, timeout=120)
+        r = subprocess.run([exe, str(n), "2000"], capture_output=True, text=True, timeout=120,
+                           env=dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(local_rank))))
+        out["c_abi"] = json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as ex:
+        out["c_abi"] = {"unavailable": repr(ex)[:200]}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -425,6 +715,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-targets", action="store_true", help="skip the north-star target block (c1 / c3 / c4 side runs)")
     ap.add_argument("--e2e-frames", type=int, default=0, help="tile-frames per e2e step (default: min(frames, 24))")
     ap.add_argument("--slab-fused", type=int, default=0, help="c5: exchange by peer stores inside K1 instead of all-to-all")
     args = ap.parse_args()
@@ -445,6 +736,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -453,117 +745,43 @@ def main():
         run_slab(args, wl, rank, world, local_rank)
         return
 
-    import watersurfacerendering_b200 as W
-    from watersurfacerendering_b200 import sharding
+    n = wl["n"]
+    res = bench_workload(args.workload, wl, args.steps, args.warmup, rank, world, local_rank, e2e_frames=args.e2e_frames)
 
-    n, F = wl["n"], wl["frames"]
-    ws = W.WSTessendorf(n, wl["L"], device=local_rank, max_tiles=wl["tiles"], max_slots=max(F, 2))
-    for j in range(wl["tiles"]):
-        prm = tile_params(wl, j)
-        ws.SetWindDirection(prm["wind"], j)
-        ws.SetWindSpeed(prm["speed"], j)
-        # every rank owns its own realisation (independent tiles / its share of the animation)
-        ws.PrepareWithGauss(gauss(n, wl["seed"] + j + 7919 * rank), tile=j)
-    # a dedicated (non-default) torch stream carries every kernel, so torch.cuda.Event brackets them
-    stream = torch.cuda.Stream(device=local_rank)
-    torch.cuda.set_stream(stream)
-    assert stream.cuda_stream != 0
-    ws.set_stream(stream.cuda_stream)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def run_steps(first, count):
-        for k in range(first, first + count):
-            t, tl = step_times(wl, k)
-            ws.compute_batch(t, tiles=tl, first_slot=0)
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        tt = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        return float(tt.item())
-
-    # ---- device-resident throughput -------------------------------------------------------------
-    run_steps(0, args.warmup)
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    l0 = ws.stats()["kernel_launches"]
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    run_steps(args.warmup, args.steps)
-    e1.record(stream)
-    barrier()
-    ms = max_over_ranks(e0.elapsed_time(e1))
-    launches = ws.stats()["kernel_launches"] - l0
-    clocks = sampler.stop() if rank == 0 else None
-    value = world * F * args.steps / (ms * 1e-3)
-
-    # ---- per-kernel timing (same steps again, CUDA events around every launch) -----------------------
-    ws.set_profiling(True)
-    run_steps(args.warmup, args.steps)
-    prof = ws.profile()
-    ws.set_profiling(False)
-    names = KERNELS
-    kms = prof["ms"]
-    dom = int(np.argmax(kms))
-    peak, peak_src = measured_peak()
-    pts = float(n) * n
-
-    def gbs(bytes_per_pt, k):
-        return bytes_per_pt * pts * prof["tile_frames"] / (kms[k] * 1e-3) / 1e9 if kms[k] > 0 else None
-
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(tpath):
+    # ---- the north-star targets that the headline workload does not show, measured in the same run -----------
+    targets = None
+    if rank == 0 and world == 1 and args.workload == "c2" and not args.no_targets:
+        targets = {}
         try:
-            traffic = json.load(open(tpath)).get(args.workload, {}).get(names[dom])
-        except Exception:
-            traffic = None
-    achieved = gbs(BYTES_PER_POINT[names[dom]], dom)
-    roofline = {
-        "bound": "hbm", "kernel": {"K1": "wso_pass1_kernel (evolve + first transform)",
-                                   "K2h": "wso_heights_kernel (height extrema)",
-                                   "K2": "wso_pass2_kernel (second transform + pack)"}[names[dom]],
-        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
-        "peak_source": peak_src, "traffic": traffic,
-        "algorithmic_bytes_per_launch": BYTES_PER_POINT[names[dom]] * pts * prof["tile_frames"] / max(prof["launches"], 1),
-        "avg_launch_ms": kms[dom] / max(prof["launches"], 1),
-        "timing": "cudaEvent pairs around every launch on the compute stream, separate pass over the same K steps",
-        "kernel_ms": dict(zip(names, kms)),
-        "kernel_share": dict(zip(names, [x / sum(kms) for x in kms])),
-        "per_kernel_achieved_gbs": {nm: gbs(BYTES_PER_POINT[nm], i) for i, nm in enumerate(names)},
-        "survey_model_achieved_gbs": gbs(SURVEY_BYTES_PER_POINT[names[dom]], dom),
-        "whole_path_gbs": sum(BYTES_PER_POINT.values()) * pts * world * F * args.steps / (ms * 1e-3) / 1e9,
-    }
-
-    # ---- end to end: host output buffers, D2H inside the timed region ---------------------------------
-    Fe = args.e2e_frames or min(F, 24)
-    disp = W.PinnedBuffer((Fe, n, n, 4))
-    norm = W.PinnedBuffer((Fe, n, n, 4))
-
-    def e2e_step(k):
-        t, tl = step_times(wl, k)
-        a, mn, mx = ws.compute_to_host(t[:Fe], disp.array, norm.array, tiles=None if tl is None else tl[:Fe])
-        return a
-
-    for k in range(args.warmup):
-        e2e_step(k)
-    barrier()
-    t0 = time.perf_counter()
-    for k in range(args.warmup, args.warmup + args.steps):
-        amps = e2e_step(k)
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    barrier()
-    e2e_val = world * Fe * args.steps / e2e_s
-    all_amps = sharding.gather_in_global_order(amps.tolist(), Fe * world, rank, world) if world > 1 else amps
+            lat = c1_latency(local_rank)
+            cabi = lat.get("c_abi") or {}
+            # device time of ONE isolated 512^2 tile-frame: through the C ABI when tools/lat_bench built, else through
+            # the Python binding (whose event records add a few microseconds around the three launches)
+            targets["c1_isolated_us"] = cabi.get("isolated_us_median", lat["isolated_us_median"])
+            targets["c1_isolated_us_python_binding"] = lat["isolated_us_median"]
+            targets["c1_back_to_back_us"] = cabi.get("back_to_back_us_per_frame", lat["back_to_back_us_python_binding"])
+            targets["c1_back_to_back_us_python_binding"] = lat["back_to_back_us_python_binding"]
+            targets["c1_detail"] = lat
+        except Exception as ex:
+            targets["c1_error"] = repr(ex)[:300]
+        try:
+            r3 = bench_workload("c3", dict(WORKLOADS["c3"]), 3, 3, rank, world, local_rank, want_e2e=False, clocks=False)
+            rf = r3["roofline"]
+            targets.update({"c3_us_per_tile_frame": r3["us_per_tile_frame"], "c3_tile_frames_s": r3["value"],
+                            "c3_frac_Balg": rf["whole_path_frac_survey_model"],
+                            "c3_frac_design": rf["whole_path_frac_design_bytes"],
+                            "c3_frac_dram_measured": rf["whole_path_frac_dram_measured"],
+                            "c3_k1_frac_design": rf["per_kernel_achieved_gbs"]["K1"] / rf["peak"],
+                            "c3_kernel_ms": rf["kernel_ms"]})
+        except Exception as ex:
+            targets["c3_error"] = repr(ex)[:300]
+        try:
+            r4 = bench_workload("c4", dict(WORKLOADS["c4"]), 5, 3, rank, world, local_rank, want_e2e=False, clocks=False)
+            targets.update({"c4_tile_frames_s": r4["value"], "c4_us_per_tile_frame": r4["us_per_tile_frame"]})
+        except Exception as ex:
+            targets["c4_error"] = repr(ex)[:300]
+        targets["north_star"] = {"c1": "<= 20 us per 512^2 tile (all maps)", "c3": ">= 0.60 of the HBM roofline at 2048^2",
+                                 "c4": "near-linear 1->8 GPU scaling for batched tiles"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -573,30 +791,31 @@ def main():
             cpu = {"value": None, "unit": "tile-frames/s", "cores": 0, "kind": "unavailable", "sample": repr(ex)}
 
     if rank == 0:
+        tiled = wl["tiles"] > 1
         line = {
-            "metric": "ocean tile-frames/s", "value": value, "unit": "tile-frames/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "metric": "ocean tile-frames/s", "value": res["value"], "unit": "tile-frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms"] / args.steps,
+            "higher_is_better": True, "scaling": "strong" if tiled else "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": wl["desc"], "tile_size": n, "frames_per_step_per_gpu": F,
-                       "chunk_tile_frames_per_launch": ws.stats()["chunk"],
-                       "l2": f"outputs of one step = {F} slots x {32 * n * n / 1e6:.0f} MB > 126 MB L2; h0 is "
-                             "resident by design (same spectrum every frame)",
-                       "parallelism": f"frames sharded per GPU x{world}, no collective"},
-            "us_per_tile_frame": ms * 1e3 / (F * args.steps),
-            "e2e": {"value": e2e_val, "unit": "tile-frames/s", "h2d_bytes_per_step": int(4 * Fe),
-                    "d2h_bytes_per_step": int(2 * 16 * n * n * Fe + 12 * Fe), "frames_per_step_per_gpu": Fe,
-                    "api": "wso_compute_to_host (C ABI), pinned host maps, copies overlapped with the next chunk",
-                    "last_amplitude": float(all_amps[-1])},
-            "gpu_launches": int(launches),
-            "roofline": roofline,
+            "config": {"workload": wl["desc"], "tile_size": n,
+                       "frames_per_step_per_gpu": res["frames_per_step_local"],
+                       "frames_per_step_all_gpus": res["frames_per_step_all"],
+                       "chunk_tile_frames_per_launch": res["chunk"],
+                       "l2": f"outputs of one step = {res['frames_per_step_local']} slots x {32 * n * n / 1e6:.0f} MB > 126 MB L2;"
+                             " h0 is resident by design (same spectrum every frame)",
+                       "parallelism": (f"{wl['tiles']} tiles sharded j mod {world} ({res['tiles_local']} per GPU) x "
+                                       f"{wl.get('times_per_step', 1)} time steps, no collective") if tiled
+                       else f"frames sharded per GPU x{world}, no collective"},
+            "us_per_tile_frame": res["us_per_tile_frame"],
+            "e2e": res.get("e2e"),
+            "gpu_launches": res["launches"],
+            "roofline": res["roofline"],
+            "targets": targets,
+            "host_cpus_bound": (f"{numa[0]}-{numa[-1]} ({len(numa)} CPUs next to GPU {local_rank})" if numa else None),
             "cpu_baseline": cpu,
-            "clocks": clocks,
+            "clocks": res["clocks"],
         }
         print(json.dumps(line), flush=True)
-    disp.close()
-    norm.close()
-    ws.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
