@@ -206,11 +206,14 @@ WSO_API int wso_get_profile(wso_ctx* ctx, double* kernel_ms3, uint64_t* launches
  * 1024^2, WaterSurfaceMesh.h:45-46 - the arithmetic is the same ComputeWaves, WSTessendorf.cpp:284-441).
  * Rank r evolves and transforms (along m) the column pairs (n, N-n) for n in [r*N/2P, (r+1)*N/2P) and, after the
  * exchange, transforms (along n) and packs the rows m' and N-m' for m' in the same range.  Per tile-frame:
- *     wso_slab_pass1(t)  ->  exchange  ->  wso_slab_heights  ->  all-reduce (min, max)  ->  wso_slab_pass2
- * The exchange is either (fused) done by pass1 itself, whose stores go straight into the owners' receive buffers
- * through NVLink peer mappings (wso_slab_ipc_handle / wso_slab_open_peer / wso_slab_set_fused) followed by any
- * inter-rank barrier, or (unfused) ONE all-to-all of the `world` equal blocks of the send buffer into the receive
- * buffer, issued by the caller (e.g. torch.distributed.all_to_all_single over NCCL) on the slab's stream.
+ *     wso_slab_pass1(t)  ->  wso_slab_exchange  ->  wso_slab_heights  ->  all-reduce (min, max)  ->  wso_slab_pass2
+ * pass1 stores what it separates where its threads hold it (coalesced); wso_slab_exchange is ONE transposing kernel
+ * that carries the Hl x Hl blocks to the owners of the row items in 256-byte rows:
+ *   fused   - straight into the owners' receive buffers over NVLink peer mappings (wso_slab_ipc_handle /
+ *             wso_slab_open_peer / wso_slab_set_fused), followed by any stream-ordered inter-rank barrier of the caller's;
+ *             the receive buffers alternate by frame parity, so frames may be enqueued back to back without host syncs;
+ *   unfused - into the `world` equal blocks of the local send buffer, which the caller then moves with ONE all-to-all
+ *             into the receive buffer (e.g. torch.distributed.all_to_all_single over NCCL) on the slab's stream.
  * The all-reduce (min over [0], max over [1] of the 2-float minmax buffer) is the caller's as well. */
 typedef struct wso_slab wso_slab;
 WSO_API int wso_slab_create(const wso_params* p, int device, uint32_t rank, uint32_t world, wso_slab** out);
@@ -235,6 +238,13 @@ WSO_API int wso_slab_set_fused(wso_slab* s, int on);
 /* Use the two-CTA cluster variant of K2 (always used at 16384, where a line pair exceeds one SM's shared memory). */
 WSO_API int wso_slab_force_pair(wso_slab* s, int on);
 WSO_API int wso_slab_pass1(wso_slab* s, float t);
+WSO_API int wso_slab_exchange(wso_slab* s);
+/* Pipelined form of the two calls above: packed fields [field0, field0 + nfields) only (whole field groups,
+ * wso_slab_fields_per_group), the exchange on `cuda_stream` (NULL = the slab's stream), so that the transfer of one field
+ * overlaps the transform of the next.  wso_slab_pass1_fields with field0 == 0 starts a new tile-frame. */
+WSO_API int wso_slab_pass1_fields(wso_slab* s, float t, int field0, int nfields);
+WSO_API int wso_slab_exchange_fields(wso_slab* s, int field0, int nfields, void* cuda_stream);
+WSO_API int wso_slab_fields_per_group(const wso_slab* s);
 WSO_API int wso_slab_heights(wso_slab* s);
 WSO_API int wso_slab_pass2(wso_slab* s);
 WSO_API int wso_slab_sync(wso_slab* s);

@@ -171,15 +171,127 @@ def test_slab_world1_2048_vs_oracle_and_batched_path(pair):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("fused", [0, 1])
-def test_slab_two_gpus_vs_oracle(fused, tmp_path):
-    """2 ranks under torchrun: all-to-all (NCCL) and fused peer-store exchange, N = 2048 vs the oracle."""
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs >= 2 GPUs")
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("fused", [0, 1, 3])
+def test_slab_multi_gpu_vs_oracle(fused, world, tmp_path):
+    """2 / 4 / 8 ranks under torchrun (as many as the box has): exchange kernel + NCCL all-to-all, and exchange kernel with
+    direct peer stores over NVLink (fused 1; 3 = issued field by field on a second stream behind K1); N = 2048 vs the oracle,
+    including three frames enqueued without host syncs."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs >= {world} GPUs")
     out = tmp_path / "res.txt"
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "slab_worker.py"), "--size", "2048",
-           "--fused", str(fused), "--out", str(out)]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
+           "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "slab_worker.py"), "--size", "2048",
+           "--fused", str(min(fused, 1)), "--pipeline", str(1 if fused == 3 else 0), "--out", str(out)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert out.read_text().strip() == "ok", out.read_text()
+
+
+# --------------------------------------------------------------------------------------------------- 16384^2
+def _huge_ok():
+    if os.environ.get("WSO_SKIP_HUGE") == "1":
+        return "WSO_SKIP_HUGE=1"
+    try:
+        import psutil
+        if psutil.virtual_memory().available < 28 << 30:
+            return "needs ~28 GB of host memory"
+    except Exception:
+        pass
+    if torch.cuda.is_available() and torch.cuda.mem_get_info(0)[0] < 40 << 30:
+        return "needs ~40 GB of device memory"
+    return None
+
+
+@pytest.mark.gpu
+def test_slab_16384_sampled_texels_symmetry_parseval():
+    """BASELINE configs[4] at FULL size (16384^2, the slab kernels incl. the two-CTA cluster K2 and the exchange kernel, one
+    rank): SURVEY 8(d)'s size-independent checks -
+      (i)   64 output texels (8 rows x 8 columns incl. 0, N/2, N-1) of height, Dx and slope-x against a direct float64
+            evaluation of the Fourier sum  out[m'][n'] = (-1)^(m'+n') Re sum_{m,n} X[m][n] e^{+2 pi i (m m' + n n')/N}
+            (reference: WSTessendorf.cpp:292-336 for X, :338-378 + :385-437 for the transform, sign and packing);
+      (ii)  the point symmetry of SURVEY 4-7: height even, Dx / Dz / slopes odd under (m,n) -> (-m,-n) mod N, bit for bit;
+      (iii) Parseval on the height field: sum out^2 = N^2 sum |even(X)|^2, even(X)[k] = (X[k] + conj X[-k]) / 2.
+    The spectrum is the counter-based one (identical on host and device, wso_counter_h0)."""
+    why = _huge_ok()
+    if why:
+        pytest.skip(why)
+    from watersurfacerendering_b200 import _lib as L
+    from watersurfacerendering_b200.slab import SlabBackend, SlabOcean, counter_h0
+    n, seed, t = 16384, 7, np.float32(10.0)
+    length = 32000.0
+    b = SlabBackend(n, length, 0, 1, 0)
+    try:
+        b.prepare_counter_device(seed)
+        ocean = SlabOcean(b)
+        ocean.compute(float(t))
+        b.sync()
+        amp, mn, mx = b.read_heights()
+        rows = b.row_index().astype(np.int64)
+        inv_rows = np.empty(n, np.int64)
+        inv_rows[rows] = np.arange(n)
+        disp = b.local_rows(L.WSO_MAP_DISPLACEMENT)   # [local row][n][4], local row r = global row rows[r]
+        norm = b.local_rows(L.WSO_MAP_NORMAL)
+        lam = float(b.params.lambda_) if hasattr(b.params, "lambda_") else -1.0
+    finally:
+        b.close()
+    assert np.isfinite(amp) and amp > 0 and amp == max(abs(mn), abs(mx))
+    # (ii) point symmetry, bit for bit (row N-m of global row m; column N-n)
+    gm = np.array([0, 1, 5, 4095, 8191, 8192, 8193, 12000, 16383])
+    for m in gm:
+        ra, rb = disp[inv_rows[m]], disp[inv_rows[(n - m) % n]]
+        na, nb = norm[inv_rows[m]], norm[inv_rows[(n - m) % n]]
+        mirror = (n - np.arange(n)) % n
+        assert np.array_equal(ra[:, 1], rb[mirror, 1]), f"height not even at row {m}"
+        assert np.array_equal(ra[:, 0], -rb[mirror, 0]) and np.array_equal(ra[:, 2], -rb[mirror, 2]), f"Dx/Dz not odd at row {m}"
+        assert np.array_equal(na[:, 0], -nb[mirror, 0]) and np.array_equal(na[:, 1], -nb[mirror, 1]), f"slopes not odd at row {m}"
+        assert np.array_equal(na[:, 2], nb[mirror, 2]) and np.array_equal(na[:, 3], nb[mirror, 3])
+    assert np.all(disp[..., 3] == 1.0)
+    # host side: X = h~(k, t) row chunk by row chunk in float64 (phase = the reference's single fp32 product omega*t)
+    pr = L.WsoParams()
+    import ctypes
+    L.load().wso_default_params(ctypes.byref(pr))
+    pr.tile_size, pr.tile_length = n, length
+    idx = np.arange(n, dtype=np.float32)
+    kv = (np.pi * (np.float32(2) * idx - np.float32(n)).astype(np.float64) / np.float64(np.float32(length))).astype(np.float32).astype(np.float64)
+    cols = np.array([0, 1, 37, 4096, 8191, 8192, 12345, 16383])
+    trow = np.array([0, 3, 64, 5000, 8192, 8193, 11111, 16383])
+    En = np.exp(2j * np.pi * np.outer(np.arange(n), cols) / n)           # [n][8]
+    acc = {k: np.zeros((len(trow), len(cols)), np.complex128) for k in ("h", "dx", "sx")}
+    Xall = np.empty((n, n), np.complex64)
+    chunk = 256
+    for m0 in range(0, n, chunk):
+        h0 = counter_h0(pr, seed, m0, chunk)
+        ph = (h0["omega"] * t).astype(np.float64)                          # fl32(omega * t), WSTessendorf.h:267
+        c, s = np.cos(ph), np.sin(ph)
+        a = h0["re"].astype(np.float64) + 1j * h0["im"].astype(np.float64)
+        ac = h0["re_c"].astype(np.float64) + 1j * h0["im_c"].astype(np.float64)
+        X = a * (c + 1j * s) + ac * (c - 1j * s)                            # WaveHeightFT, WSTessendorf.h:265-275
+        Xall[m0:m0 + chunk] = X.astype(np.complex64)
+        kx = kv[None, :]
+        kz = kv[m0:m0 + chunk, None]
+        kl = np.sqrt(kx * kx + kz * kz)
+        ux = np.where(kl > 1e-5, kx / np.where(kl > 1e-5, kl, 1.0), 0.0)
+        Em = np.exp(2j * np.pi * np.outer(trow, np.arange(m0, m0 + chunk)) / n)   # [8][chunk]
+        acc["h"] += Em @ (X @ En)
+        acc["dx"] += Em @ ((-1j * ux * X) @ En)                           # cpp:316-323
+        acc["sx"] += Em @ ((1j * kx * X) @ En)                            # cpp:304-307
+    sign = np.where((trow[:, None] + cols[None, :]) % 2 == 0, 1.0, -1.0)
+    ref_h, ref_dx, ref_sx = sign * acc["h"].real, sign * acc["dx"].real, sign * acc["sx"].real
+    got = disp[inv_rows[trow]][:, cols, :]
+    gnorm = norm[inv_rows[trow]][:, cols, :]
+    # the parity gate's max-abs tolerance: 1e-4 x the channel's range over the whole map
+    rng_h = float(mx) - float(mn)
+    rng_dx = float(disp[..., 0].max()) - float(disp[..., 0].min())
+    rng_sx = float(norm[..., 0].max()) - float(norm[..., 0].min())
+    assert np.abs(got[..., 1].astype(np.float64) * float(amp) - ref_h).max() <= 1e-4 * rng_h
+    assert np.abs(got[..., 0].astype(np.float64) - lam * ref_dx).max() <= 1e-4 * rng_dx
+    assert np.abs(gnorm[..., 0].astype(np.float64) - ref_sx).max() <= 1e-4 * rng_sx
+    # (iii) Parseval on the height field
+    Xm = Xall[(n - np.arange(n)) % n][:, (n - np.arange(n)) % n]
+    even_sq = 0.0
+    for m0 in range(0, n, 1024):
+        y = 0.5 * (Xall[m0:m0 + 1024].astype(np.complex128) + np.conj(Xm[m0:m0 + 1024].astype(np.complex128)))
+        even_sq += float(np.sum(y.real ** 2 + y.imag ** 2))
+    out_sq = float(np.sum((disp[..., 1].astype(np.float64) * float(amp)) ** 2))
+    assert abs(out_sq - float(n) * n * even_sq) <= 2e-4 * out_sq, (out_sq, float(n) * n * even_sq)

@@ -101,6 +101,10 @@ SYMBOLS = {
     "wso_slab_set_fused": (_int, [_vp, _int]),
     "wso_slab_force_pair": (_int, [_vp, _int]),
     "wso_slab_pass1": (_int, [_vp, _f32]),
+    "wso_slab_exchange": (_int, [_vp]),
+    "wso_slab_pass1_fields": (_int, [_vp, _f32, _int, _int]),
+    "wso_slab_exchange_fields": (_int, [_vp, _int, _int, _vp]),
+    "wso_slab_fields_per_group": (_int, [_vp]),
     "wso_slab_heights": (_int, [_vp]),
     "wso_slab_pass2": (_int, [_vp]),
     "wso_slab_sync": (_int, [_vp]),

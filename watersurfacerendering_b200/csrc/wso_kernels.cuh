@@ -73,6 +73,13 @@ struct LaunchArgsT {
     int slab_shift;
     int slab_rank;
     float2* Wdst[8];
+    // Slab K1, staged store (NULL: store through Wdst in the exchange layout right away).  K1 writes what it separates
+    // where consecutive threads hold consecutive m': stage[f][half][jl][m'], m' over the WHOLE half spectrum - contiguous
+    // 8-byte stores - and the transposing exchange kernel (wso_slab_kernels.cu) carries the Hl x Hl blocks to their
+    // owners in 256-byte rows.  (The direct layout costs one 32-byte sector per 8 useful bytes when a line is so long
+    // that a CTA holds a single column pair)
+    float2* slab_stage;
+    int slab_field0;  // slab K1 launched field group by field group (exchange pipelined behind it): first field group
     BatchItem items[CAP];
     // the tile constants of every item travel by value in the kernel parameters (constant bank): no dependent
     // global load sits between CTA start and the first h0 request
@@ -678,12 +685,18 @@ struct Pass1 {
                 }
                 const int f = by * NF + fl;
                 if constexpr (SLAB) {
-                    // the store IS the transpose: block of the device that owns row item m'
                     const int hl_log = LOGN - 1 - args.slab_shift;
                     const int Hl = 1 << hl_log;
-                    float2* dst = args.Wdst[mp >> hl_log] + ((size_t)((mp & (Hl - 1)) * 4 + f) * 2) * Hl + jl;
-                    dst[0] = wa;
-                    dst[Hl] = wb;
+                    if (args.slab_stage != nullptr) {
+                        float2* dst = args.slab_stage + ((size_t)(f * 2) * Hl + jl) * H + mp;
+                        dst[0] = wa;
+                        dst[(size_t)Hl * H] = wb;
+                    } else {
+                        // the store IS the transpose: block of the device that owns row item m'
+                        float2* dst = args.Wdst[mp >> hl_log] + ((size_t)((mp & (Hl - 1)) * 4 + f) * 2) * Hl + jl;
+                        dst[0] = wa;
+                        dst[Hl] = wb;
+                    }
                 } else if constexpr (WLayout<LOGN>::paired) {
                     float4* dst = reinterpret_cast<float4*>(Wit + ((size_t)mp * 4 + f) * N) + jl;
                     *dst = make_float4(wa.x, wa.y, wb.x, wb.y);

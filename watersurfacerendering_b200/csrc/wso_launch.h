@@ -33,8 +33,17 @@ cudaError_t launch_warp_core(int logn, int which, const LaunchArgs& args, int n_
 // Slab-decomposed path (one grid over several devices).  phase 0: K1 on this device's column pairs,
 // 1: K2h on its row items, 2: K2 (pair = force the two-CTA cluster variant; always used when a line pair exceeds
 // one SM's shared memory).
-cudaError_t launch_slab_phase(int logn, int phase, const LaunchArgsT<1>& args, bool pair, cudaStream_t stream);
+// nfields (phase 0 only): 0 = all four packed fields, else that many from field args.slab_field0 * NF on
+cudaError_t launch_slab_phase(int logn, int phase, const LaunchArgsT<1>& args, bool pair, int nfields, cudaStream_t stream);
+int slab_fields_per_group(int logn);
 bool slab_size_supported(int logn);
+// The slab exchange as one transposing kernel (wso_slab_kernels.cu): stage = K1's staged output on this device, dst.p[d]
+// = where device d's row items go (block `src = this device` of d's receive buffer, or of a local send buffer).
+struct XposeDst {
+    float2* p[8];
+};
+cudaError_t launch_slab_exchange(const float2* stage, const XposeDst& dst, int world, int hl_log, int h_log, int field0,
+                                 int nfields, cudaStream_t stream);
 
 // Prepare() on the device (wso_prepare_kernels.cu).  One launch builds the per-point records
 // h0[jl][half][m] and the pair-summed records hs[jl][i][2] of the column pairs j0 .. j0+n_pairs-1.

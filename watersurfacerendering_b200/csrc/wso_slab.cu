@@ -35,8 +35,10 @@ struct wso_slab {
     float4* d_hs = nullptr;   // [hl][n/2][2]
     float* d_kv = nullptr;    // [n]
     float2* d_tw = nullptr;   // [n]
-    float2* d_send = nullptr; // [world][hl][4][2][hl]   (unused in fused mode)
-    float2* d_recv = nullptr; // [world][hl][4][2][hl]
+    float2* d_stage = nullptr;  // K1's staged output [4][2][hl][n/2] (coalesced stores; hl >= 32)
+    float2* d_send = nullptr;   // [world][hl][4][2][hl]: what the exchange kernel fills when a collective library moves the blocks
+    float2* d_recv = nullptr;   // 2 x [world][hl][4][2][hl]: receive buffers by frame parity (direct peer stores), else the first
+    uint64_t frame = 0;         // tile-frames started (wso_slab_pass1)
     float4* d_disp = nullptr; // [2*hl][n]
     float4* d_norm = nullptr;
     float* d_minmax = nullptr;  // [2]
@@ -153,20 +155,34 @@ int upload_local(wso_slab* s, RecordAt&& record_at) {
     return WSO_OK;
 }
 
+// Receive buffer of the current frame.  With direct peer stores a rank may already write frame f+1 into its peers while
+// they still transform frame f (the last collective of a frame, the min/max all-reduce, precedes K2): the buffers
+// alternate by frame parity.  A frame f+2 store cannot overtake K2 of frame f: the writer has passed the all-reduce of
+// frame f+1 by then, which the reader only enters after its K2h(f+1), stream-ordered behind its K2(f).
+inline size_t recv_offset(const wso_slab* s) { return s->fused ? (size_t)(s->frame & 1) * block_elems(s) * s->world : 0; }
+inline bool staged(const wso_slab* s) { return s->hl >= 32; }
+
+// where this rank's separated half-spectra go, per owner d of the row items
+void exchange_dst(const wso_slab* s, float2* (&dst)[8]) {
+    const size_t blk = block_elems(s);
+    for (uint32_t d = 0; d < 8; ++d) dst[d] = nullptr;
+    for (uint32_t d = 0; d < s->world; ++d)
+        dst[d] = s->fused ? s->peers[d] + recv_offset(s) + (size_t)s->rank * blk
+               : (s->world == 1 ? s->d_recv : s->d_send + (size_t)d * blk);  // one rank: nothing to exchange
+}
+
 void fill_args(const wso_slab* s, SlabArgs& a, float t) {
     std::memset(&a, 0, sizeof(a));
     a.tw = s->d_tw;
-    a.W = s->d_recv;
+    a.W = s->d_recv + recv_offset(s);
+    a.slab_stage = staged(s) ? s->d_stage : nullptr;
     a.disp = s->d_disp;
     a.norm = s->d_norm;
     a.minmax = s->d_minmax;
     a.amp_out = s->d_ampl;
     a.slab_shift = s->shift;
     a.slab_rank = (int)s->rank;
-    const size_t blk = block_elems(s);
-    for (uint32_t d = 0; d < s->world; ++d)
-        a.Wdst[d] = s->fused ? s->peers[d] + (size_t)s->rank * blk
-                  : (s->world == 1 ? s->d_recv : s->d_send + (size_t)d * blk);  // one rank: nothing to exchange
+    exchange_dst(s, a.Wdst);
     a.items[0].tile = 0;
     a.items[0].slot = 0;
     a.items[0].t = t;
@@ -214,8 +230,9 @@ int wso_slab_create(const wso_params* p, int device, uint32_t rank, uint32_t wor
         SLAB_CUDA(s, cudaMalloc(&s->d_hs, sizeof(float4) * (size_t)s->hl * (n / 2) * 2));
         SLAB_CUDA(s, cudaMalloc(&s->d_kv, sizeof(float) * n));
         SLAB_CUDA(s, cudaMalloc(&s->d_tw, sizeof(float2) * n));
+        SLAB_CUDA(s, cudaMalloc(&s->d_stage, sizeof(float2) * blk * world));
         SLAB_CUDA(s, cudaMalloc(&s->d_send, sizeof(float2) * blk * world));
-        SLAB_CUDA(s, cudaMalloc(&s->d_recv, sizeof(float2) * blk * world));
+        SLAB_CUDA(s, cudaMalloc(&s->d_recv, sizeof(float2) * blk * world * 2));
         SLAB_CUDA(s, cudaMalloc(&s->d_disp, sizeof(float4) * (size_t)2 * s->hl * n));
         SLAB_CUDA(s, cudaMalloc(&s->d_norm, sizeof(float4) * (size_t)2 * s->hl * n));
         SLAB_CUDA(s, cudaMalloc(&s->d_minmax, sizeof(float) * 2));
@@ -245,7 +262,7 @@ int wso_slab_destroy(wso_slab* s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     for (void* p : s->opened) cudaIpcCloseMemHandle(p);
     cudaFree(s->d_h0); cudaFree(s->d_hs); cudaFree(s->d_kv); cudaFree(s->d_tw);
-    cudaFree(s->d_send); cudaFree(s->d_recv); cudaFree(s->d_disp); cudaFree(s->d_norm);
+    cudaFree(s->d_stage); cudaFree(s->d_send); cudaFree(s->d_recv); cudaFree(s->d_disp); cudaFree(s->d_norm);
     cudaFree(s->d_minmax); cudaFree(s->d_ampl);
     cudaFreeHost(s->h_small);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
@@ -396,13 +413,16 @@ int wso_slab_set_fused(wso_slab* s, int on) {
     return WSO_OK;
 }
 
-static int slab_phase(wso_slab* s, int phase) {
+static int slab_phase(wso_slab* s, int phase, int field0 = 0, int nfields = 0) {
     if (!s) return WSO_ERR_INVALID_ARG;
     if (!s->prepared) return sfail(s, WSO_ERR_NOT_PREPARED, "slab: no spectrum (wso_slab_prepare_counter / wso_slab_import_h0)");
     SLAB_CUDA(s, cudaSetDevice(s->device));
     SlabArgs a;
     fill_args(s, a, s->last_t);
-    cudaError_t e = wso::launch_slab_phase(s->logn, phase, a, s->force_pair, s->stream);
+    const int nf = wso::slab_fields_per_group(s->logn);
+    if (nfields > 0 && (field0 % nf != 0 || nfields % nf != 0)) return sfail(s, WSO_ERR_INVALID_ARG, "slab: field range must cover whole field groups");
+    a.slab_field0 = field0 / nf;
+    cudaError_t e = wso::launch_slab_phase(s->logn, phase, a, s->force_pair, nfields, s->stream);
     if (e != cudaSuccess) return sfail_cuda(s, e, "slab kernel launch");
     return WSO_OK;
 }
@@ -410,7 +430,43 @@ static int slab_phase(wso_slab* s, int phase) {
 int wso_slab_pass1(wso_slab* s, float t) {
     if (!s) return WSO_ERR_INVALID_ARG;
     s->last_t = t;
+    s->frame += 1;
     return slab_phase(s, 0);
+}
+
+// The exchange step: one transposing kernel carries K1's staged output to the owners of the row items - straight into
+// their receive buffers over NVLink peer memory (wso_slab_set_fused), or into the blocks of the local send buffer that a
+// collective library then moves.  A no-op for grids too small to stage (K1 has stored in the exchange layout itself).
+int wso_slab_exchange(wso_slab* s) { return wso_slab_exchange_fields(s, 0, 4, nullptr); }
+
+// Pipelined form: pass1 and the exchange field by field, so that the transfer of field f overlaps the transform of field
+// f+1 - the caller enqueues wso_slab_pass1_fields(t, f, k) on the slab's stream and wso_slab_exchange_fields(f, k, xs) on
+// a second stream xs that it has ordered behind the pass1 launch (event).  Fields must come as whole field groups
+// (wso_slab_fields_per_group: 1 for the production sizes).
+int wso_slab_pass1_fields(wso_slab* s, float t, int field0, int nfields) {
+    if (!s || field0 < 0 || nfields < 1 || field0 + nfields > 4) return WSO_ERR_INVALID_ARG;
+    if (field0 == 0) {
+        s->last_t = t;
+        s->frame += 1;
+    }
+    return slab_phase(s, 0, field0, nfields);
+}
+
+int wso_slab_fields_per_group(const wso_slab* s) { return s ? wso::slab_fields_per_group(s->logn) : 4; }
+
+int wso_slab_exchange_fields(wso_slab* s, int field0, int nfields, void* cuda_stream) {
+    if (!s || field0 < 0 || nfields < 1 || field0 + nfields > 4) return WSO_ERR_INVALID_ARG;
+    if (!s->prepared) return sfail(s, WSO_ERR_NOT_PREPARED, "slab: no spectrum (wso_slab_prepare_counter / wso_slab_import_h0)");
+    if (!staged(s)) return WSO_OK;
+    SLAB_CUDA(s, cudaSetDevice(s->device));
+    wso::XposeDst dst;
+    exchange_dst(s, dst.p);
+    int hl_log = 0;
+    while ((1u << hl_log) < s->hl) ++hl_log;
+    cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : s->stream;
+    cudaError_t e = wso::launch_slab_exchange(s->d_stage, dst, (int)s->world, hl_log, s->logn - 1, field0, nfields, st);
+    if (e != cudaSuccess) return sfail_cuda(s, e, "slab exchange kernel launch");
+    return WSO_OK;
 }
 int wso_slab_heights(wso_slab* s) { return slab_phase(s, 1); }
 int wso_slab_pass2(wso_slab* s) { return slab_phase(s, 2); }

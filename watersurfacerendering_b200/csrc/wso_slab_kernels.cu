@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(Pass1<LOGN, SlabCfg<LOGN>::CP, SlabCfg<LOGN>::
 wso_slab_pass1_kernel(const __grid_constant__ SlabArgs args) {
     extern __shared__ __align__(16) float2 smem[];
     DeviceExec ex;
-    Pass1<LOGN, SlabCfg<LOGN>::CP, SlabCfg<LOGN>::NF, true>::run(ex, smem, blockIdx.x, blockIdx.y, 0, args);
+    Pass1<LOGN, SlabCfg<LOGN>::CP, SlabCfg<LOGN>::NF, true>::run(ex, smem, blockIdx.x, blockIdx.y + args.slab_field0, 0, args);
 }
 
 template <int LOGN>
@@ -73,13 +73,48 @@ wso_slab_pass2_pair_kernel(const __grid_constant__ SlabArgs args) {
     cluster.sync();  // the partner may still be reading this CTA's line
 }
 
+// The exchange step of the slab path as ONE kernel over peer memory: tile transposes of the staged K1 output
+//   stage[f][half][jl][d*Hl + ml]  (this device, coalesced by K1)   ->   W_d[src][ml][f][half][jl]  (owner d of row item ml)
+// where W_d is the receive buffer of device d - mapped peer memory over NVLink (CUDA IPC) or, when the exchange is left to
+// a collective library, this device's block d of a send buffer.  Reads and writes are 256-byte rows of a 32 x 32 tile
+// (8-byte elements) through a padded shared-memory tile; blockIdx.z = (d, f, half).
+__global__ void __launch_bounds__(256) wso_slab_exchange_kernel(const float2* __restrict__ stage, XposeDst dst, int hl_log,
+                                                                int h_log, int z0) {
+    __shared__ float2 tile[32][33];
+    const int Hl = 1 << hl_log;
+    const int z = blockIdx.z + z0;
+    const int d = z >> 3, fh = z & 7;  // destination device, (f, half)
+    const int jl0 = blockIdx.y * 32, ml0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    const float2* src = stage + (((size_t)fh << hl_log) << h_log) + ((size_t)d << hl_log);
+#pragma unroll
+    for (int r = 0; r < 32; r += 8) tile[ty + r][tx] = src[((size_t)(jl0 + ty + r) << h_log) + ml0 + tx];
+    __syncthreads();
+    float2* out = dst.p[d] + ((size_t)fh << hl_log);
+#pragma unroll
+    for (int r = 0; r < 32; r += 8) out[(((size_t)(ml0 + ty + r) * 8) << hl_log) + jl0 + tx] = tile[tx][ty + r];
+    (void)Hl;
+}
+
+cudaError_t launch_slab_exchange(const float2* stage, const XposeDst& dst, int world, int hl_log, int h_log, int field0,
+                                 int nfields, cudaStream_t stream) {
+    const int Hl = 1 << hl_log;
+    if (Hl < 32 || field0 < 0 || nfields < 1 || field0 + nfields > 4) return cudaErrorInvalidValue;
+    // blockIdx.z enumerates (d, f, half) = d*8 + f*2 + half: one launch per destination covers the fields [field0, +n)
+    for (int d = 0; d < world; ++d) {
+        wso_slab_exchange_kernel<<<dim3(Hl / 32, Hl / 32, nfields * 2), 256, 0, stream>>>(stage, dst, hl_log, h_log,
+                                                                                         d * 8 + field0 * 2);
+    }
+    return cudaGetLastError();
+}
+
 template <class Kern>
 static cudaError_t opt_in_smem(Kern kern, int bytes) {
     return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 
 template <int LOGN>
-static cudaError_t slab_launch(int phase, const SlabArgs& args, bool pair, cudaStream_t stream) {
+static cudaError_t slab_launch(int phase, const SlabArgs& args, bool pair, int nfields, cudaStream_t stream) {
     using C = SlabCfg<LOGN>;
     using P1 = Pass1<LOGN, C::CP, C::NF, true>;
     using PH = Pass2<LOGN, C::RH, true, true>;
@@ -90,7 +125,10 @@ static cudaError_t slab_launch(int phase, const SlabArgs& args, bool pair, cudaS
     cudaError_t e;
     if (phase == 0) {
         if ((e = opt_in_smem(wso_slab_pass1_kernel<LOGN>, P1::SMEM_BYTES)) != cudaSuccess) return e;
-        wso_slab_pass1_kernel<LOGN><<<dim3(Hl / C::CP, 4 / C::NF, 1), P1::T, P1::SMEM_BYTES, stream>>>(args);
+        // nfields packed fields from field group args.slab_field0 on (all of them: slab_nfields == 0)
+        const int groups = nfields > 0 ? nfields / C::NF : 4 / C::NF;
+        if (groups < 1 || (nfields > 0 && nfields % C::NF != 0)) return cudaErrorInvalidValue;
+        wso_slab_pass1_kernel<LOGN><<<dim3(Hl / C::CP, groups, 1), P1::T, P1::SMEM_BYTES, stream>>>(args);
     } else if (phase == 1) {
         if ((e = opt_in_smem(wso_slab_heights_kernel<LOGN>, PH::SMEM_BYTES)) != cudaSuccess) return e;
         wso_slab_heights_kernel<LOGN><<<dim3(Hl / C::RH, 1, 1), PH::T, PH::SMEM_BYTES, stream>>>(args);
@@ -119,15 +157,27 @@ static cudaError_t slab_launch(int phase, const SlabArgs& args, bool pair, cudaS
     return cudaGetLastError();
 }
 
-cudaError_t launch_slab_phase(int logn, int phase, const LaunchArgsT<1>& args, bool pair, cudaStream_t stream) {
+int slab_fields_per_group(int logn) {
+    switch (logn) {
+        case 6: return SlabCfg<6>::NF;
+        case 8: return SlabCfg<8>::NF;
+        case 11: return SlabCfg<11>::NF;
+        case 12: return SlabCfg<12>::NF;
+        case 13: return SlabCfg<13>::NF;
+        case 14: return SlabCfg<14>::NF;
+        default: return 4;
+    }
+}
+
+cudaError_t launch_slab_phase(int logn, int phase, const LaunchArgsT<1>& args, bool pair, int nfields, cudaStream_t stream) {
     switch (logn) {
 #ifndef WSO_ONLY_LOGN
-        case 6: return slab_launch<6>(phase, args, pair, stream);
-        case 8: return slab_launch<8>(phase, args, pair, stream);
-        case 11: return slab_launch<11>(phase, args, pair, stream);
-        case 12: return slab_launch<12>(phase, args, pair, stream);
-        case 13: return slab_launch<13>(phase, args, pair, stream);
-        case 14: return slab_launch<14>(phase, args, pair, stream);
+        case 6: return slab_launch<6>(phase, args, pair, nfields, stream);
+        case 8: return slab_launch<8>(phase, args, pair, nfields, stream);
+        case 11: return slab_launch<11>(phase, args, pair, nfields, stream);
+        case 12: return slab_launch<12>(phase, args, pair, nfields, stream);
+        case 13: return slab_launch<13>(phase, args, pair, nfields, stream);
+        case 14: return slab_launch<14>(phase, args, pair, nfields, stream);
 #endif
         default: return cudaErrorInvalidValue;
     }

@@ -4,9 +4,12 @@ One process per GPU (torchrun).  Rank r owns the column pairs (n, N-n), n in [r*
 transform (along m, fused with the spectrum evolve: kernel K1) and the row pairs (m', N-m') of the same range for
 the second (along n, fused with the packing: K2h, K2).  In between sits the ONE exchange step of the path:
 
-  * ``fused=True``  — K1's stores go straight into the owners' receive buffers through NVLink peer mappings
-    (CUDA IPC); the collective that follows (the min/max all-reduce needs one anyway) orders the ranks.
-  * ``fused=False`` — K1 fills a send buffer and ``torch.distributed.all_to_all_single`` (NCCL) transposes it.
+K1 stores its output coalesced; ONE transposing exchange kernel (``wso_slab_exchange``) carries the blocks to the owners:
+
+  * ``fused=True``  — straight into the owners' receive buffers through NVLink peer mappings (CUDA IPC): the exchange IS
+    the kernel's stores; a stream-ordered collective on a scratch word orders the ranks afterwards.  The receive buffers
+    alternate by frame parity, so ``compute()`` may be called back to back without host synchronisation.
+  * ``fused=False`` — into the blocks of a local send buffer that ``torch.distributed.all_to_all_single`` (NCCL) moves.
 
 and one 2-float all-reduce, because the normalisation amplitude A = max(|min|,|max|) of the height field is global
 (reference: WSTessendorf.cpp:440-455).  torch is plumbing here (process group, streams); every kernel is in
@@ -108,6 +111,20 @@ class SlabBackend:
     def pass1(self, t: float):
         L.check_slab(self._lib.wso_slab_pass1(self._h, float(t)), self._h)
 
+    def exchange(self):
+        """The transposing exchange kernel (peer stores in fused mode, else it fills the send blocks)."""
+        L.check_slab(self._lib.wso_slab_exchange(self._h), self._h)
+
+    def pass1_fields(self, t: float, field0: int, nfields: int):
+        L.check_slab(self._lib.wso_slab_pass1_fields(self._h, float(t), int(field0), int(nfields)), self._h)
+
+    def exchange_fields(self, field0: int, nfields: int, cuda_stream_ptr: Optional[int] = None):
+        L.check_slab(self._lib.wso_slab_exchange_fields(self._h, int(field0), int(nfields),
+                                                        C.c_void_p(cuda_stream_ptr or 0)), self._h)
+
+    def fields_per_group(self) -> int:
+        return int(self._lib.wso_slab_fields_per_group(self._h))
+
     def heights(self):
         L.check_slab(self._lib.wso_slab_heights(self._h), self._h)
 
@@ -144,11 +161,14 @@ def counter_h0(params: "L.WsoParams", seed: int, m0: int, rows: int) -> np.ndarr
 class SlabOcean:
     """ComputeWaves(t) of one N x N grid over the ranks of a torch.distributed process group."""
 
-    def __init__(self, backend, group=None, fused: bool = False):
+    def __init__(self, backend, group=None, fused: bool = False, pipeline: bool = False):
         import torch.distributed as dist
         self.b = backend
         self.group = group
         self.world = backend.world
+        self._bound_stream = None
+        self._xs = None
+        self.pipeline = pipeline
         self.fused = bool(fused) and self.world > 1
         if self.world > 1 and not dist.is_initialized():
             raise RuntimeError("SlabOcean over several ranks needs an initialised torch.distributed process group")
@@ -163,7 +183,29 @@ class SlabOcean:
         import torch
         import torch.distributed as dist
         b = self.b
-        b.pass1(t)
+        # the library's kernels and the collectives below must share one stream: bind the backend to torch's current
+        # stream (a change of stream drains the old one first)
+        cur = torch.cuda.current_stream().cuda_stream if torch.cuda.is_available() else None
+        if cur is not None and cur != self._bound_stream and hasattr(b, "set_stream"):
+            b.set_stream(cur)
+            self._bound_stream = cur
+        if self.fused and self.pipeline and hasattr(b, "pass1_fields") and b.fields_per_group() == 1 and b.hl >= 32:
+            # field by field: the peer stores of field f (second stream) overlap the transform of field f + 1
+            main = torch.cuda.current_stream()
+            if self._xs is None:
+                self._xs = torch.cuda.Stream(device=main.device)
+                self._evs = [torch.cuda.Event() for _ in range(5)]
+            for f in range(4):
+                b.pass1_fields(t, f, 1)
+                self._evs[f].record(main)
+                self._xs.wait_event(self._evs[f])
+                b.exchange_fields(f, 1, self._xs.cuda_stream)
+            self._evs[4].record(self._xs)
+            main.wait_event(self._evs[4])
+        else:
+            b.pass1(t)
+            if hasattr(b, "exchange"):  # (the emulated CPU backend's pass1 fills the send blocks itself)
+                b.exchange()
         if self.world > 1 and not self.fused:
             dist.all_to_all_single(b.recv, b.send, group=self.group)
         b_needs_order = self.world > 1 and self.fused
