@@ -4,7 +4,7 @@
 TAG=$1; N=$2
 OUT=gpurun_out/$TAG; mkdir -p $OUT
 if [ "$3" != skiptests ]; then
-  timeout 900 python -m pytest tests/test_slab.py -m gpu -x -q -k "multi_gpu" > $OUT/pytest_slab_multi.log 2>&1; echo "pytest rc=$?"; tail -n 4 $OUT/pytest_slab_multi.log
+  timeout 900 python -m pytest tests/test_slab.py -m gpu -x -q -k "multi_gpu and ${3:-vs_oracle}" > $OUT/pytest_slab_multi.log 2>&1; echo "pytest rc=$?"; tail -n 4 $OUT/pytest_slab_multi.log
 fi
 RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N"
 for fused in 0 1; do

@@ -42,8 +42,8 @@ bool slab_size_supported(int logn);
 struct XposeDst {
     float2* p[8];
 };
-cudaError_t launch_slab_exchange(const float2* stage, const XposeDst& dst, int world, int hl_log, int h_log, int field0,
-                                 int nfields, cudaStream_t stream);
+cudaError_t launch_slab_exchange(const float2* stage, const XposeDst& dst, int world, int rank, int hl_log, int h_log,
+                                 int field0, int nfields, cudaStream_t stream);
 
 // Prepare() on the device (wso_prepare_kernels.cu).  One launch builds the per-point records
 // h0[jl][half][m] and the pair-summed records hs[jl][i][2] of the column pairs j0 .. j0+n_pairs-1.

@@ -464,7 +464,7 @@ int wso_slab_exchange_fields(wso_slab* s, int field0, int nfields, void* cuda_st
     int hl_log = 0;
     while ((1u << hl_log) < s->hl) ++hl_log;
     cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : s->stream;
-    cudaError_t e = wso::launch_slab_exchange(s->d_stage, dst, (int)s->world, hl_log, s->logn - 1, field0, nfields, st);
+    cudaError_t e = wso::launch_slab_exchange(s->d_stage, dst, (int)s->world, (int)s->rank, hl_log, s->logn - 1, field0, nfields, st);
     if (e != cudaSuccess) return sfail_cuda(s, e, "slab exchange kernel launch");
     return WSO_OK;
 }

@@ -77,13 +77,17 @@ wso_slab_pass2_pair_kernel(const __grid_constant__ SlabArgs args) {
 //   stage[f][half][jl][d*Hl + ml]  (this device, coalesced by K1)   ->   W_d[src][ml][f][half][jl]  (owner d of row item ml)
 // where W_d is the receive buffer of device d - mapped peer memory over NVLink (CUDA IPC) or, when the exchange is left to
 // a collective library, this device's block d of a send buffer.  Reads and writes are 256-byte rows of a 32 x 32 tile
-// (8-byte elements) through a padded shared-memory tile; blockIdx.z = (d, f, half).
+// (8-byte elements) through a padded shared-memory tile.
 __global__ void __launch_bounds__(256) wso_slab_exchange_kernel(const float2* __restrict__ stage, XposeDst dst, int hl_log,
-                                                                int h_log, int z0) {
+                                                                int h_log, int fh0, int world_log, int rank) {
     __shared__ float2 tile[32][33];
     const int Hl = 1 << hl_log;
-    const int z = blockIdx.z + z0;
-    const int d = z >> 3, fh = z & 7;  // destination device, (f, half)
+    // blockIdx.z = ((f - field0) * 2 + half) * world + i: the destinations rotate fastest and start behind this device, so
+    // that at any moment the P devices store to P different owners (all NVLink ingress ports busy, no incast on one)
+    const int world = 1 << world_log;
+    const int i = blockIdx.z & (world - 1);
+    const int d = (rank + 1 + i) & (world - 1);
+    const int fh = (blockIdx.z >> world_log) + fh0;  // (f, half)
     const int jl0 = blockIdx.y * 32, ml0 = blockIdx.x * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
     const float2* src = stage + (((size_t)fh << hl_log) << h_log) + ((size_t)d << hl_log);
@@ -96,15 +100,14 @@ __global__ void __launch_bounds__(256) wso_slab_exchange_kernel(const float2* __
     (void)Hl;
 }
 
-cudaError_t launch_slab_exchange(const float2* stage, const XposeDst& dst, int world, int hl_log, int h_log, int field0,
-                                 int nfields, cudaStream_t stream) {
+cudaError_t launch_slab_exchange(const float2* stage, const XposeDst& dst, int world, int rank, int hl_log, int h_log,
+                                 int field0, int nfields, cudaStream_t stream) {
     const int Hl = 1 << hl_log;
     if (Hl < 32 || field0 < 0 || nfields < 1 || field0 + nfields > 4) return cudaErrorInvalidValue;
-    // blockIdx.z enumerates (d, f, half) = d*8 + f*2 + half: one launch per destination covers the fields [field0, +n)
-    for (int d = 0; d < world; ++d) {
-        wso_slab_exchange_kernel<<<dim3(Hl / 32, Hl / 32, nfields * 2), 256, 0, stream>>>(stage, dst, hl_log, h_log,
-                                                                                         d * 8 + field0 * 2);
-    }
+    int world_log = 0;
+    while ((1 << world_log) < world) ++world_log;
+    wso_slab_exchange_kernel<<<dim3(Hl / 32, Hl / 32, nfields * 2 * world), 256, 0, stream>>>(stage, dst, hl_log, h_log,
+                                                                                             field0 * 2, world_log, rank);
     return cudaGetLastError();
 }
 
