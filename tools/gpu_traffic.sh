@@ -1,14 +1,15 @@
 #!/bin/bash
 # Dev tool (under gpurun, one GPU): DRAM bytes per kernel launch with the caches left alone between kernels
-# (ncu --cache-control none), for a list of WL:MASK:MB[:EXTRAENV] configurations.   usage: gpu_traffic.sh TAG cfg...
+# (ncu --cache-control none), for a list of WL:MASK:MB[:EXTRAENV] configurations (MASK d = the default kernel choice).   usage: gpu_traffic.sh TAG cfg...
 TAG=$1; shift
 OUT=gpurun_out/$TAG; mkdir -p $OUT
 for cfg in "$@"; do
   IFS=: read wl m mb extra <<< "$cfg"
   name=${wl}_m${m}_mb${mb}${extra:+_$extra}
-  env $extra WSO_WARP_CORE=$m WSO_W_BUDGET_MB=$mb timeout 200 ncu --cache-control none --clock-control none \
+  maskenv="WSO_WARP_CORE=$m"; [ "$m" = d ] && maskenv="WSO_DEFAULT_KERNELS=1"   # d = the built-in choice per size
+  env $extra $maskenv WSO_W_BUDGET_MB=$mb timeout 200 ncu --cache-control none --clock-control none \
     --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,lts__t_sectors_op_read.sum,lts__t_sectors_op_write.sum \
-    -k regex:wso_ -s 45 -c 48 --csv --log-file $OUT/traffic_$name.csv python bench.py --workload $wl --steps 2 --warmup 3 --no-cpu-baseline > $OUT/traffic_$name.log 2>&1
+    -k regex:wso_ -s 45 -c 48 --csv --log-file $OUT/traffic_$name.csv python bench.py --workload $wl --steps 2 --warmup 3 --no-cpu-baseline --no-targets > $OUT/traffic_$name.log 2>&1
   python - "$OUT/traffic_$name.csv" "$name" <<'PY'
 import csv, sys, collections
 rows = [r for r in csv.reader(open(sys.argv[1])) if len(r) > 10]

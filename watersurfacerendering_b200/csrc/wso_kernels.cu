@@ -197,21 +197,33 @@ static cudaError_t launch_tiled_jacobian(const Args& args, int n_items, cudaStre
     }
 }
 
+// Experiment hook: request at least this much dynamic shared memory for K1 / K2 (bytes; 0 = what the kernel needs).  A
+// larger request lowers the number of CTAs of that kernel an SM can hold and leaves threads / registers / shared memory
+// for the CTAs of the OTHER compute lane's kernel, i.e. it forces K1 and K2 of different chunks to share SMs.
+static int exp_min_smem(const char* name) {
+    const char* env = std::getenv(name);
+    const int v = env ? std::atoi(env) : 0;
+    return v > 0 && v <= 227 * 1024 ? v : 0;
+}
+
 template <int LOGN, class TL, class Args>
 static cudaError_t launch_tiled(const Args& args, int n_items, cudaStream_t stream, cudaEvent_t* ev) {
     using P1 = Pass1<LOGN, TL::CP, TL::NF>;
     using P2 = Pass2<LOGN, TL::RI, false>;
     using PH = Pass2<LOGN, TL::RH, true>;
+    static const int k1_min = exp_min_smem("WSO_EXP_K1_SMEM"), k2_min = exp_min_smem("WSO_EXP_K2_SMEM");
+    const int smem1 = P1::SMEM_BYTES > k1_min ? P1::SMEM_BYTES : k1_min;
+    const int smem2 = P2::SMEM_BYTES > k2_min ? P2::SMEM_BYTES : k2_min;
     static std::atomic<bool> configured[16];  // per device: opt in to > 48 KB of dynamic shared memory once
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 16 || !configured[dev].load(std::memory_order_acquire)) {
         cudaError_t e;
-        e = cudaFuncSetAttribute(wso_pass1_kernel<LOGN, TL, Args, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P1::SMEM_BYTES);
+        e = cudaFuncSetAttribute(wso_pass1_kernel<LOGN, TL, Args, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(wso_pass1_kernel<LOGN, TL, Args, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P1::SMEM_BYTES);
+        e = cudaFuncSetAttribute(wso_pass1_kernel<LOGN, TL, Args, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(wso_pass2_kernel<LOGN, TL, Args>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2::SMEM_BYTES);
+        e = cudaFuncSetAttribute(wso_pass2_kernel<LOGN, TL, Args>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(wso_heights_kernel<LOGN, TL, Args>, cudaFuncAttributeMaxDynamicSharedMemorySize, PH::SMEM_BYTES);
         if (e != cudaSuccess) return e;
@@ -235,8 +247,8 @@ static cudaError_t launch_tiled(const Args& args, int n_items, cudaStream_t stre
         if (warp_mask & 1) e = launch_warp_core(LOGN, 0, args, n_items, stream);
     }
     if (!(warp_mask & 1))
-        e = fast ? launch_pdl(wso_pass1_kernel<LOGN, TL, Args, true>, g1, P1::T, P1::SMEM_BYTES, stream, args)
-                 : launch_pdl(wso_pass1_kernel<LOGN, TL, Args, false>, g1, P1::T, P1::SMEM_BYTES, stream, args);
+        e = fast ? launch_pdl(wso_pass1_kernel<LOGN, TL, Args, true>, g1, P1::T, smem1, stream, args)
+                 : launch_pdl(wso_pass1_kernel<LOGN, TL, Args, false>, g1, P1::T, smem1, stream, args);
     if (e != cudaSuccess) return e;
     if (ev) cudaEventRecord(ev[1], stream);
     const dim3 gh(PH::H / TL::RH, 1, n_items);
@@ -250,7 +262,7 @@ static cudaError_t launch_tiled(const Args& args, int n_items, cudaStream_t stre
     if constexpr (std::is_same<Args, LaunchArgs>::value) {
         if (warp_mask & 4) e = launch_warp_core(LOGN, 2, args, n_items, stream);
     }
-    if (!(warp_mask & 4)) e = launch_pdl(wso_pass2_kernel<LOGN, TL, Args>, g2, P2::T, P2::SMEM_BYTES, stream, args);
+    if (!(warp_mask & 4)) e = launch_pdl(wso_pass2_kernel<LOGN, TL, Args>, g2, P2::T, smem2, stream, args);
     if (e != cudaSuccess) return e;
     if (ev) cudaEventRecord(ev[3], stream);
     return cudaGetLastError();
