@@ -9,6 +9,10 @@
 
 namespace wso {
 
+#ifndef WSO_K2_SPLIT_DEFAULT
+#define WSO_K2_SPLIT_DEFAULT 0
+#endif
+
 // CTA tiling.  CP: column pairs per K1 CTA, NF: packed fields per K1 CTA, RI: row items (each = output rows m'
 // and N-m') per K2 CTA, RH: row items per K2h CTA (one line each).  CTA threads = lines * N / 16.
 template <int CP_, int NF_, int RI_, int RH_>
@@ -100,6 +104,37 @@ wso_pass2_kernel(const __grid_constant__ Args args) {
     extern __shared__ __align__(16) float2 smem[];
     DeviceExec ex;
     Pass2<LOGN, TL::RI, false>::run(ex, smem, blockIdx.x, blockIdx.y, blockIdx.z, args);
+}
+
+// "K2nh": the height pre-pass and the NORMAL map in one launch (blockIdx.y = 0: normal-map CTAs, 1: height CTAs), followed
+// by wso_pass2_kernel for the displacement map only.  The normal map does not need the amplitude A, so K2h - a partial
+// wave of latency-bound CTAs when launched alone - runs underneath the store-bound normal-map CTAs instead of in front of
+// both maps.  Needs equal CTA sizes of the two bodies.
+template <int LOGN, class TL>
+struct K2Split {
+    using P2 = Pass2<LOGN, TL::RI, false>;
+    static constexpr int RHS = 2 * TL::RI;  // a height CTA holds as many lines as a map CTA: equal CTA sizes
+    static constexpr bool possible = (RHS <= P2::H) && (RHS * P2::N / kValsPerThread <= 1024);
+    using PH = Pass2<LOGN, possible ? RHS : 1, true>;
+    static constexpr int SMEM = P2::SMEM_BYTES > PH::SMEM_BYTES ? P2::SMEM_BYTES : PH::SMEM_BYTES;
+    static constexpr int GX = P2::H / TL::RI;  // >= the number of height CTAs, H / (2 RI)
+};
+template <int LOGN, class TL, class Args>
+__global__ void __launch_bounds__(Pass2<LOGN, TL::RI, false>::T, min_blocks(Pass2<LOGN, TL::RI, false>::T))
+wso_pass2nh_kernel(const __grid_constant__ Args args) {
+    extern __shared__ __align__(16) float2 smem[];
+    DeviceExec ex;
+    if (blockIdx.y == 0) {
+        if (blockIdx.x >= Pass2<LOGN, TL::RI, false>::H / TL::RI) return;
+        // K1 (the predecessor in the stream) must have completed before W is read
+        ex.pdl_wait();
+        ex.pdl_release();
+        Pass2<LOGN, TL::RI, false>::run(ex, smem, blockIdx.x, 1, blockIdx.z, args);
+    } else {
+        using PH = typename K2Split<LOGN, TL>::PH;
+        if (blockIdx.x >= PH::H / K2Split<LOGN, TL>::RHS) return;
+        PH::run(ex, smem, blockIdx.x, 0, blockIdx.z, args);
+    }
 }
 
 // K2 with the Jacobian channel: one row item (all four packed fields) per CTA, both maps from one CTA.
@@ -197,6 +232,21 @@ static cudaError_t launch_tiled_jacobian(const Args& args, int n_items, cudaStre
     }
 }
 
+// K2h together with the normal map (wso_pass2nh_kernel) instead of in front of both maps: WSO_K2_SPLIT=0/1 overrides.
+static std::atomic<int> g_k2_split_override{-1};
+void set_k2_split_override(int on) { g_k2_split_override.store(on < 0 ? -1 : (on ? 1 : 0), std::memory_order_relaxed); }
+static bool k2_split_enabled() {
+    static const int env = [] {
+        const char* e = std::getenv("WSO_K2_SPLIT");
+        return e ? (std::atoi(e) != 0 ? 1 : 0) : -1;
+    }();
+    const int forced = g_k2_split_override.load(std::memory_order_relaxed);
+    if (forced >= 0) return forced != 0;
+    if (env >= 0) return env != 0;
+    return WSO_K2_SPLIT_DEFAULT != 0;
+}
+bool k2_split_active() { return k2_split_enabled(); }
+
 // Experiment hook: request at least this much dynamic shared memory for K1 / K2 (bytes; 0 = what the kernel needs).  A
 // larger request lowers the number of CTAs of that kernel an SM can hold and leaves threads / registers / shared memory
 // for the CTAs of the OTHER compute lane's kernel, i.e. it forces K1 and K2 of different chunks to share SMs.
@@ -227,6 +277,11 @@ static cudaError_t launch_tiled(const Args& args, int n_items, cudaStream_t stre
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(wso_heights_kernel<LOGN, TL, Args>, cudaFuncAttributeMaxDynamicSharedMemorySize, PH::SMEM_BYTES);
         if (e != cudaSuccess) return e;
+        if constexpr (K2Split<LOGN, TL>::possible) {
+            const int smemnh = K2Split<LOGN, TL>::SMEM > k2_min ? K2Split<LOGN, TL>::SMEM : k2_min;
+            e = cudaFuncSetAttribute(wso_pass2nh_kernel<LOGN, TL, Args>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemnh);
+            if (e != cudaSuccess) return e;
+        }
         if (dev >= 0 && dev < 16) configured[dev].store(true, std::memory_order_release);
     }
     cudaError_t e;
@@ -251,6 +306,19 @@ static cudaError_t launch_tiled(const Args& args, int n_items, cudaStream_t stre
                  : launch_pdl(wso_pass1_kernel<LOGN, TL, Args, false>, g1, P1::T, smem1, stream, args);
     if (e != cudaSuccess) return e;
     if (ev) cudaEventRecord(ev[1], stream);
+    if constexpr (K2Split<LOGN, TL>::possible) {
+        if (!(warp_mask & 6) && k2_split_enabled()) {
+            using KS = K2Split<LOGN, TL>;
+            const int smemnh = KS::SMEM > k2_min ? KS::SMEM : k2_min;
+            e = launch_pdl(wso_pass2nh_kernel<LOGN, TL, Args>, dim3(KS::GX, 2, n_items), P2::T, smemnh, stream, args);
+            if (e != cudaSuccess) return e;
+            if (ev) cudaEventRecord(ev[2], stream);
+            e = launch_pdl(wso_pass2_kernel<LOGN, TL, Args>, dim3(P2::H / TL::RI, 1, n_items), P2::T, smem2, stream, args);
+            if (e != cudaSuccess) return e;
+            if (ev) cudaEventRecord(ev[3], stream);
+            return cudaGetLastError();
+        }
+    }
     const dim3 gh(PH::H / TL::RH, 1, n_items);
     if constexpr (std::is_same<Args, LaunchArgs>::value) {
         if (warp_mask & 2) e = launch_warp_core(LOGN, 1, args, n_items, stream);

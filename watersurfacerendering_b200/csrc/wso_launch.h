@@ -28,6 +28,9 @@ int kernels_per_launch();
 bool warp_core_supported(int logn);
 // process-wide override of the kernel-set choice (bit k = kernel k on the warp-per-line set; -1 = built-in default)
 void set_warp_core_override(int mask);
+// K2h launched together with the normal map, the displacement map behind them (-1 = built-in default); what is active now
+void set_k2_split_override(int on);
+bool k2_split_active();
 cudaError_t launch_warp_core(int logn, int which, const LaunchArgs& args, int n_items, cudaStream_t stream);
 
 // Slab-decomposed path (one grid over several devices).  phase 0: K1 on this device's column pairs,
