@@ -111,11 +111,21 @@ WSO_API int wso_prepare_counter(wso_ctx* ctx, uint32_t tile, uint64_t seed);
  * (tile_length in particular) were set beforehand; this is also the checkpoint/restore mechanism. */
 WSO_API int wso_import_h0(wso_ctx* ctx, uint32_t tile, const wso_h0_record* h0);
 WSO_API int wso_export_h0(const wso_ctx* ctx, uint32_t tile, wso_h0_record* h0);
+/* Compact form, 12 bytes per wave vector (amp.re, amp.im, dispersion), row-major [m][n]: heightAmp_conj == conj(heightAmp)
+ * in every reference-built h0 (WSTessendorf.cpp:132-135), so nothing is lost against the 20-byte BaseWaveHeight record. */
+WSO_API int wso_import_h0_compact(wso_ctx* ctx, uint32_t tile, const float* h0_3f);
+WSO_API int wso_export_h0_compact(const wso_ctx* ctx, uint32_t tile, float* h0_3f);
 
 /* Replaces: float WSTessendorf::ComputeWaves(float t) (WSTessendorf.cpp:284-441) for tile 0 -> slot 0.
  * Blocking.  On return both maps are in pinned host memory (wso_map_host) and on the device
  * (wso_map_device); *amplitude receives the return value A. */
 WSO_API int wso_compute(wso_ctx* ctx, float t, float* amplitude);
+/* The same frame without the host copy and without blocking: tile 0 -> device slot 0 on the context's stream.  *event_out
+ * is a cudaEvent_t (as void*) owned by the context and valid until the next call; it completes when both maps, A and
+ * min/max of the frame are final on the device (wso_map_device, wso_read_heights).  A CUDA caller orders its own stream
+ * behind it with cudaStreamWaitEvent; wso_wait_event blocks the host. */
+WSO_API int wso_compute_async(wso_ctx* ctx, float t, void** event_out);
+WSO_API int wso_wait_event(wso_ctx* ctx, void* event);
 
 /* Batched form: n tile-frames.  Item i evolves tile tiles[i] (NULL = all tile 0) to time t[i] and writes
  * device map slot first_slot + i.  Asynchronous on the context's stream; results stay on the device. */

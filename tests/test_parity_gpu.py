@@ -255,6 +255,30 @@ def test_maps_hold_reference_defaults_before_first_compute(wso):
         assert np.all(d == 0.0) and np.all(nm[..., 1] == 1.0) and np.all(nm[..., [0, 2, 3]] == 0.0)
 
 
+def test_compact_h0_and_async_compute(wso):
+    """the 12-byte spectrum record (amp, dispersion; heightAmp_conj is redundant, WSTessendorf.cpp:132-135)
+    round-trips bit for bit against the 20-byte one, and the asynchronous frame (event instead of a blocking call with a
+    host copy) produces the same device maps as ComputeWaves."""
+    n = 128
+    p, o, xi = _oracle_for(n)
+    with wso.WSTessendorf(n, p.tile_length, max_slots=2) as ws:
+        ws.PrepareWithGauss(xi)
+        full = ws.ExportH0()
+        comp = ws.ExportH0Compact()
+        assert np.array_equal(comp[..., 0], full["re"]) and np.array_equal(comp[..., 1], full["im"])
+        assert np.array_equal(comp[..., 2], full["omega"])
+        a1 = ws.ComputeWaves(5.5)
+        d1, n1 = ws.GetDisplacements().copy(), ws.GetNormals().copy()
+        with wso.WSTessendorf(n, p.tile_length, max_slots=2) as ws2:
+            ws2.ImportH0Compact(comp)
+            assert ws2.ExportH0().tobytes() == full.tobytes()
+            ev = ws2.ComputeWavesAsync(5.5)
+            ws2.WaitEvent(ev)
+            a2, mn2, mx2 = ws2.read_heights(0, 1)
+            assert a2[0] == a1
+            assert ws2.copy_map(0, 0).tobytes() == d1.tobytes() and ws2.copy_map(1, 0).tobytes() == n1.tobytes()
+
+
 def test_independent_tiles_in_one_batch(wso):
     """BASELINE config 4 in miniature: tiles with different wind / seed, batched in one launch."""
     n, ntiles = 128, 5

@@ -62,6 +62,10 @@ SYMBOLS = {
     "wso_prepare_counter": (_int, [_vp, _u32, C.c_uint64]),
     "wso_import_h0": (_int, [_vp, _u32, _vp]),
     "wso_export_h0": (_int, [_vp, _u32, _vp]),
+    "wso_import_h0_compact": (_int, [_vp, _u32, _vp]),
+    "wso_export_h0_compact": (_int, [_vp, _u32, _vp]),
+    "wso_compute_async": (_int, [_vp, _f32, C.POINTER(_vp)]),
+    "wso_wait_event": (_int, [_vp, _vp]),
     "wso_compute": (_int, [_vp, _f32, C.POINTER(_f32)]),
     "wso_compute_batch": (_int, [_vp, _u32, _vp, _vp, _u32]),
     "wso_compute_to_host": (_int, [_vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -50,6 +50,7 @@ struct wso_ctx {
     cudaEvent_t ev_lane_join[2] = {nullptr, nullptr};
     int lanes = 2;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_async = nullptr;  // wso_compute_async
     cudaStream_t stream = nullptr;  // the one kernels run on (own_stream unless wso_set_stream)
     cudaEvent_t ev_chunk[2] = {nullptr, nullptr};
     cudaEvent_t ev_copied[2] = {nullptr, nullptr};
@@ -624,6 +625,7 @@ int wso_destroy(wso_ctx* c) {
     free_device_buffers(c);
     for (int i = 0; i < 2; ++i)
         if (c->ext_sem[i]) cudaDestroyExternalSemaphore(c->ext_sem[i]);
+    if (c->ev_async) cudaEventDestroy(c->ev_async);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
@@ -753,6 +755,61 @@ int wso_export_h0(const wso_ctx* c, uint32_t tile, wso_h0_record* h0) {
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     cudaFree(d_out);
     return e == cudaSuccess ? WSO_OK : WSO_ERR_CUDA;
+}
+
+// Compact form of the spectrum: heightAmp_conj == conj(heightAmp) in every reference-built h0
+// (WSTessendorf.cpp:132-135), so 12 bytes per wave vector - (amp.re, amp.im, dispersion) - carry all of it.
+int wso_import_h0_compact(wso_ctx* c, uint32_t tile, const float* h0_3f) {
+    int rc = begin_prepare(c, tile);
+    if (rc != WSO_OK) return rc;
+    if (!h0_3f) return fail(c, WSO_ERR_INVALID_ARG, "h0 is NULL");
+    const size_t n2 = (size_t)c->n * c->n;
+    std::vector<wso_h0_record> full(n2);
+    for (size_t i = 0; i < n2; ++i) {
+        full[i].amp_re = h0_3f[3 * i + 0];
+        full[i].amp_im = h0_3f[3 * i + 1];
+        full[i].amp_conj_re = h0_3f[3 * i + 0];
+        full[i].amp_conj_im = -h0_3f[3 * i + 1];
+        full[i].dispersion = h0_3f[3 * i + 2];
+    }
+    return upload_h0(c, tile, full.data());
+}
+
+int wso_export_h0_compact(const wso_ctx* c, uint32_t tile, float* h0_3f) {
+    if (!c || !h0_3f || tile >= c->max_tiles) return WSO_ERR_INVALID_ARG;
+    if (!c->tiles[tile].is_prepared) return WSO_ERR_NOT_PREPARED;
+    const size_t n2 = (size_t)c->n * c->n;
+    std::vector<wso_h0_record> full(n2);
+    const int rc = wso_export_h0(c, tile, full.data());
+    if (rc != WSO_OK) return rc;
+    for (size_t i = 0; i < n2; ++i) {
+        h0_3f[3 * i + 0] = full[i].amp_re;
+        h0_3f[3 * i + 1] = full[i].amp_im;
+        h0_3f[3 * i + 2] = full[i].dispersion;
+    }
+    return WSO_OK;
+}
+
+// Asynchronous ComputeWaves(t): tile 0 -> device slot 0 on the context's stream, no host copy, no synchronisation.
+// *event_out (a cudaEvent_t owned by the context, valid until the next call) completes when both maps and A are final;
+// a CUDA caller orders its own stream behind it (cudaStreamWaitEvent), any caller can block with wso_wait_event.
+int wso_compute_async(wso_ctx* c, float t, void** event_out) {
+    int rc = check_batch(c, 1, nullptr, &t, 0);
+    if (rc != WSO_OK) return rc;
+    WSO_CUDA(c, cudaSetDevice(c->device));
+    if (!c->ev_async) WSO_CUDA(c, cudaEventCreateWithFlags(&c->ev_async, cudaEventDisableTiming));
+    if ((rc = push_lambdas(c)) != WSO_OK) return rc;
+    if ((rc = enqueue_chunk(c, 1, nullptr, &t, 0, 0, c->stream)) != WSO_OK) return rc;
+    WSO_CUDA(c, cudaEventRecord(c->ev_async, c->stream));
+    if (event_out) *event_out = c->ev_async;
+    return WSO_OK;
+}
+
+int wso_wait_event(wso_ctx* c, void* event) {
+    if (!c || !event) return WSO_ERR_INVALID_ARG;
+    WSO_CUDA(c, cudaSetDevice(c->device));
+    WSO_CUDA(c, cudaEventSynchronize(static_cast<cudaEvent_t>(event)));
+    return WSO_OK;
 }
 
 int wso_compute_batch(wso_ctx* c, uint32_t n, const uint32_t* tiles, const float* t, uint32_t first_slot) {

@@ -187,6 +187,27 @@ class WSTessendorf:
         L.check(self._lib.wso_export_h0(self._h, tile, _ptr(h0)), self._h)
         return h0
 
+    def ImportH0Compact(self, h0_3f: np.ndarray, tile: int = 0):
+        """(N,N,3) fp32 (amp.re, amp.im, dispersion): 12 bytes per wave vector instead of the reference's 20."""
+        n = self.GetTileSize(tile)
+        a = np.ascontiguousarray(h0_3f, np.float32).reshape(n, n, 3)
+        L.check(self._lib.wso_import_h0_compact(self._h, tile, _ptr(a)), self._h)
+
+    def ExportH0Compact(self, tile: int = 0) -> np.ndarray:
+        n = self.GetTileSize(tile)
+        a = np.zeros((n, n, 3), np.float32)
+        L.check(self._lib.wso_export_h0_compact(self._h, tile, _ptr(a)), self._h)
+        return a
+
+    def ComputeWavesAsync(self, t: float) -> int:
+        """Enqueue one frame (tile 0 -> device slot 0), no host copy, no synchronisation. -> cudaEvent_t handle (int)."""
+        ev = C.c_void_p()
+        L.check(self._lib.wso_compute_async(self._h, float(t), C.byref(ev)), self._h)
+        return ev.value
+
+    def WaitEvent(self, event: int):
+        L.check(self._lib.wso_wait_event(self._h, C.c_void_p(event)), self._h)
+
     # ------------------------------------------------------------------ per-frame (reference API)
     def ComputeWaves(self, t: float) -> np.float32:
         a = C.c_float()
