@@ -37,6 +37,9 @@ namespace wso {
 #ifndef WSO_V2_NBUFH
 #define WSO_V2_NBUFH 1
 #endif
+#ifndef WSO_V2_NBUF2
+#define WSO_V2_NBUF2 2  // line buffers per group of the map kernel
+#endif
 constexpr int min_blocks_for(int threads, int regs) {
     return (65536 / regs) / threads < 1 ? 1 : (65536 / regs) / threads;
 }
@@ -55,12 +58,15 @@ wso_pass1w_kernel(const __grid_constant__ Args args) {
 }
 
 // blockIdx.y: 0 = displacement map, 1 = normal map
+template <int LOGN>
+using PassM = v2::Pass2W<LOGN, Cfg2<LOGN>::GPC, WSO_V2_NBUF2>;
+
 template <int LOGN, class Args>
-__global__ void __launch_bounds__(v2::Pass2W<LOGN, Cfg2<LOGN>::GPC>::T, WSO_V2_MINB2)
+__global__ void __launch_bounds__(PassM<LOGN>::T, WSO_V2_MINB2)
 wso_pass2w_kernel(const __grid_constant__ Args args, int n_items) {
     extern __shared__ __align__(128) float2 smem[];
     DevCtx cx;
-    using P2 = v2::Pass2W<LOGN, Cfg2<LOGN>::GPC>;
+    using P2 = PassM<LOGN>;
     if (blockIdx.y == 0) P2::template run<0>(cx, smem, blockIdx.x, gridDim.x, n_items, args);
     else P2::template run<1>(cx, smem, blockIdx.x, gridDim.x, n_items, args);
 }
@@ -113,7 +119,7 @@ const DevPlan& plan_for_device() {
     DevPlan& p = plans[dev];
     if (p.ready) return p;
     using P1 = v2::Pass1W<LOGN, Cfg2<LOGN>::CP, Cfg2<LOGN>::NF>;
-    using P2 = v2::Pass2W<LOGN, Cfg2<LOGN>::GPC>;
+    using P2 = PassM<LOGN>;
     auto k1 = wso_pass1w_kernel<LOGN, LaunchArgs>;
     auto k2 = wso_pass2w_kernel<LOGN, LaunchArgs>;
     auto kh = wso_heightsw_kernel<LOGN, LaunchArgs>;
@@ -161,7 +167,7 @@ template <int LOGN>
 cudaError_t launch_k2(const LaunchArgs& args, int n_items, cudaStream_t stream) {
     const DevPlan& p = plan_for_device<LOGN>();
     if (p.err != cudaSuccess) return p.err;
-    using P2 = v2::Pass2W<LOGN, Cfg2<LOGN>::GPC>;
+    using P2 = PassM<LOGN>;
     const int units = n_items * P2::H;
     constexpr int upc = Cfg2<LOGN>::GPC / 2;  // a row item of a map occupies two line groups
     int ctas = (units + upc - 1) / upc;
