@@ -194,8 +194,11 @@ WSO_API int wso_unregister_host(void* ptr);
 /* Two implementations of the three hot-path kernels exist for 512^2, 1024^2 and 2048^2 batched launches: CTA-per-line
  * (Stockham stages through shared memory) and warp-per-line (radix-32 register stages, shuffle exchanges, bulk-copy line
  * pipeline).  They produce the same maps within the parity tolerance and share the intermediate layout.  mask bit 0 / 1 /
- * 2 puts K1 / K2h / K2 on the warp-per-line set; -1 restores the built-in choice (what measured faster per size).
- * Process-wide; meant for A/B measurements and for the parity tests, which run both sets. */
+ * 2 puts K1 / K2h / K2 on the warp-per-line set; bits 4 / 6 (0x10 / 0x40) run K1 / K2 of the CTA-per-line set in their
+ * persistent form (a fixed grid of CTAs walks the work items and requests the inputs of its next item ahead of the store
+ * phase of the current one; bit-identical results); -1 restores the built-in choice (what measured faster per size).
+ * Any other bit: WSO_ERR_INVALID_ARG.  Process-wide; meant for A/B measurements and for the parity tests, which run
+ * every form. */
 WSO_API int wso_select_kernels(int mask);
 
 /* Introspection used by the benchmark: number of kernels launched so far by this context, the chunk

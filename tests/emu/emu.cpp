@@ -13,7 +13,10 @@ using namespace wso;
 
 // JAC: the Jacobian-channel kernels: K1's general body with field 1's real slot filled, K2 with four
 // lines per CTA (by = 0 only).
-template <int LOGN, int CP, int NF, int RI, bool JAC = false>
+// PERSIST: bit 0 = K1, bit 2 = K2 through their persistent forms (run_persistent: a few emulated CTAs walk the work items,
+// each with its own shared memory and thread states that live across items - the prefetched inputs of the next item
+// sit in them while the current item is stored)
+template <int LOGN, int CP, int NF, int RI, bool JAC = false, int PERSIST = 0>
 static int run_cfg(const float* amp_t, const float* omega_t, const float* kv, float omega0, float lambda,
                    float t, float* disp, float* norm, float* minmax, float* amp_out, float* w_out) {
     constexpr int N = 1 << LOGN, H = N / 2;
@@ -86,6 +89,16 @@ static int run_cfg(const float* amp_t, const float* omega_t, const float* kv, fl
         const bool fast = !JAC && td.table_len > 0 && td.use_pairs != 0;
         std::vector<float2> smem(P1::SMEM_BYTES / sizeof(float2));
         std::vector<ThreadState> st(P1::T);
+        if constexpr ((PERSIST & 1) != 0) {
+            if (!fast) return -2;
+            const int ncta = 5;
+            for (int cta = 0; cta < ncta; ++cta) {
+                for (auto& v : smem) v = make_float2(NAN, NAN);
+                for (auto& x : st) for (auto& v : x.v) v = make_float2(NAN, NAN);
+                HostExec ex{P1::T, st.data()};
+                P1F::run_persistent(ex, smem.data(), cta, ncta, 1, args);
+            }
+        } else {
         for (int by = 0; by < 4 / NF; ++by)
             for (int bx = 0; bx < H / CP; ++bx) {
                 for (auto& v : smem) v = make_float2(NAN, NAN);
@@ -93,6 +106,7 @@ static int run_cfg(const float* amp_t, const float* omega_t, const float* kv, fl
                 if (fast) P1F::run(ex, smem.data(), bx, by, 0, args);
                 else P1::run(ex, smem.data(), bx, by, 0, args);
             }
+        }
     }
     if (w_out) std::memcpy(w_out, W.data(), W.size() * sizeof(float2));
     {   // K2h: height extrema
@@ -107,12 +121,22 @@ static int run_cfg(const float* amp_t, const float* omega_t, const float* kv, fl
     {
         std::vector<float2> smem(P2::SMEM_BYTES / sizeof(float2));
         std::vector<ThreadState> st(P2::T);
+        if constexpr ((PERSIST & 4) != 0) {
+            const int ncta = 7;
+            for (int cta = 0; cta < ncta; ++cta) {
+                for (auto& v : smem) v = make_float2(NAN, NAN);
+                for (auto& x : st) for (auto& v : x.v) v = make_float2(NAN, NAN);
+                HostExec ex{P2::T, st.data()};
+                P2::run_persistent(ex, smem.data(), cta, ncta, 1, args);
+            }
+        } else {
         for (int by = 0; by < (JAC ? 1 : 2); ++by)
             for (int bx = 0; bx < H / RI2; ++bx) {
                 for (auto& v : smem) v = make_float2(NAN, NAN);
                 HostExec ex{P2::T, st.data()};
                 P2::run(ex, smem.data(), bx, by, 0, args);
             }
+        }
     }
     return 0;
 }
@@ -420,6 +444,15 @@ extern "C" int wso_emu_compute(int logn, int variant, const float* amp_t, const 
     CFG(10, 0, 4, 2, 4)
     CFG(11, 0, 4, 1, 2)
 #undef CFG
+    // variants 200+: the persistent forms of K1 / K2 (the tilings batched launches run)
+#define PCFG(L, V, CP, NF, RI, PM) \
+    if (logn == L && variant == 200 + V) return run_cfg<L, CP, NF, RI, false, PM>(amp_t, omega_t, kv, omega0, lambda, t, disp, norm, minmax, amp_out, w_out);
+    PCFG(9, 0, 4, 4, 1, 5)
+    PCFG(9, 1, 4, 4, 1, 1)
+    PCFG(10, 0, 4, 2, 2, 5)
+    PCFG(10, 1, 4, 2, 2, 4)
+    PCFG(11, 0, 4, 2, 1, 5)
+#undef PCFG
     // variants 100+: the Jacobian-channel kernels with the same K1 / K2h tilings
 #define JCFG(L, V, CP, NF, RI) \
     if (logn == L && variant == 100 + V) return run_cfg<L, CP, NF, RI, true>(amp_t, omega_t, kv, omega0, lambda, t, disp, norm, minmax, amp_out, w_out);

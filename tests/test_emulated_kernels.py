@@ -67,6 +67,28 @@ def test_emulated_kernels_vs_oracle_large(n, variant):
     assert abs(a - a_ref) <= SCALAR_REL_TOL * a_ref
 
 
+# variants 200+: the persistent forms (Pass1::run_persistent / Pass2::run_persistent) - a few emulated CTAs walk the work
+# items with the inputs of the next item prefetched into the thread states.  Same arithmetic, different walk: the maps
+# must equal the one-CTA-per-item kernels' BIT FOR BIT (and therefore pass the oracle gate).
+@pytest.mark.parametrize("n,variant,base", [(512, 200, 0), (512, 201, 0), (1024, 200, 0), (1024, 201, 0), (2048, 200, None)])
+def test_emulated_persistent_kernels(n, variant, base):
+    rng = np.random.default_rng(n + 1)
+    xi = (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))).astype(np.complex64)
+    p = P.OceanParams(tile_size=n, tile_length=1000.0 * n / 512)
+    o = P.PortOracle(p)
+    h0 = o.prepare(xi)
+    t = 11.375
+    a, disp, norm, mn, mx, _ = E.compute(n, p.tile_length, p.lam, h0["re"], h0["im"], h0["omega"], t, variant=variant)
+    if base is not None:
+        a0, d0, n0, mn0, mx0, _ = E.compute(n, p.tile_length, p.lam, h0["re"], h0["im"], h0["omega"], t, variant=base)
+        assert (a, mn, mx) == (a0, mn0, mx0)
+        assert disp.tobytes() == d0.tobytes() and norm.tobytes() == n0.tobytes()
+    if base is None or n == 512:
+        a_ref, d_ref, n_ref = o.compute_waves(t)
+        assert_maps_close(disp, norm, d_ref, n_ref, f"N={n} persistent")
+        assert abs(a - a_ref) <= SCALAR_REL_TOL * a_ref
+
+
 def test_one_hot_layout():
     """One-hot h0 at special wave vectors (index 0 = Nyquist line, N/2 = DC line, N-1) must light up
     exactly the oracle's pattern (index / Hermitian layout check)."""

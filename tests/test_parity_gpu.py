@@ -211,7 +211,10 @@ _KERNEL_SET_REFS = {}
 
 
 @pytest.mark.parametrize("n,mask", [(512, 1), (512, 2), (512, 4), (512, 7), (1024, 0), (1024, 1), (1024, 2), (1024, 4),
-                                    (1024, 7), (2048, 3), (2048, 4), (2048, 7)])
+                                    (1024, 7), (2048, 3), (2048, 4), (2048, 7),
+                                    # bits 4 / 6: K1 / K2 of the CTA-per-line set in their persistent form
+                                    (512, 0x10), (512, 0x50), (1024, 0x10), (1024, 0x40), (1024, 0x52), (2048, 0x40),
+                                    (2048, 0)])
 def test_both_kernel_sets_vs_oracle(wso, n, mask):
     """The warp-per-line kernels (wso_kernels2.cu: radix-32 register stages, shuffle exchanges, bulk-copy line pipeline)
     against the oracle, alone and mixed kernel by kernel with the CTA-per-line set (mask bit k = kernel k on the

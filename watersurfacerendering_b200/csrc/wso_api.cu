@@ -1117,7 +1117,7 @@ int wso_alloc_host(size_t bytes, void** ptr) {
 }
 
 int wso_select_kernels(int mask) {
-    if (mask < -1 || mask > 7) return WSO_ERR_INVALID_ARG;
+    if (mask < -1 || (mask & ~0x57) != 0) return WSO_ERR_INVALID_ARG;
     wso::set_warp_core_override(mask);
     return WSO_OK;
 }

@@ -106,6 +106,47 @@ wso_pass2_kernel(const __grid_constant__ Args args) {
     Pass2<LOGN, TL::RI, false>::run(ex, smem, blockIdx.x, blockIdx.y, blockIdx.z, args);
 }
 
+// Persistent forms (Pass1::run_persistent / Pass2::run_persistent): a fixed 1-D grid of CTAs - as many as the device
+// holds at once - walks the work items of the launch and requests the inputs of its next item ahead of the store phase
+// of the current one.  Batched launches of the fused K1 tilings (512^2, 1024^2) and of the paired-W K2 (512^2 ... 2048^2).
+// experiment hook: co-resident persistent CTAs (slot = blockIdx.x / SMs) start `ns` apart so that they stay in different phases
+__device__ __forceinline__ void exp_stagger(unsigned ns) {
+    if (ns == 0) return;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    do {
+        __nanosleep(200);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    } while (t1 - t0 < ns);
+}
+template <int LOGN, class TL>
+struct PersistOk {
+    static constexpr bool k1 = Pass1<LOGN, TL::CP, TL::NF, false, true>::kPersistOk && LOGN >= 9 && LOGN <= 11;
+    static constexpr bool k2 = WLayout<LOGN>::paired && LOGN >= 9 && LOGN <= 11;
+};
+template <int LOGN, class TL, class Args>
+__global__ void __launch_bounds__(Pass1<LOGN, TL::CP, TL::NF>::T, min_blocks(Pass1<LOGN, TL::CP, TL::NF>::T))
+wso_pass1p_kernel(const __grid_constant__ Args args, const int n_items) {
+    extern __shared__ __align__(16) float2 smem[];
+    DeviceExec ex;
+#ifdef WSO_EXP_P_STAGGER1_NS
+    exp_stagger((blockIdx.x / 148u) * (unsigned)(WSO_EXP_P_STAGGER1_NS));
+#endif
+    if constexpr (PersistOk<LOGN, TL>::k1)
+        Pass1<LOGN, TL::CP, TL::NF, false, true>::run_persistent(ex, smem, blockIdx.x, gridDim.x, n_items, args);
+}
+template <int LOGN, class TL, class Args>
+__global__ void __launch_bounds__(Pass2<LOGN, TL::RI, false>::T, min_blocks(Pass2<LOGN, TL::RI, false>::T))
+wso_pass2p_kernel(const __grid_constant__ Args args, const int n_items) {
+    extern __shared__ __align__(16) float2 smem[];
+    DeviceExec ex;
+#ifdef WSO_EXP_P_STAGGER2_NS
+    exp_stagger((blockIdx.x / 148u) * (unsigned)(WSO_EXP_P_STAGGER2_NS));
+#endif
+    if constexpr (PersistOk<LOGN, TL>::k2)
+        Pass2<LOGN, TL::RI, false>::run_persistent(ex, smem, blockIdx.x, gridDim.x, n_items, args);
+}
+
 // "K2nh": the height pre-pass and the NORMAL map in one launch (blockIdx.y = 0: normal-map CTAs, 1: height CTAs), followed
 // by wso_pass2_kernel for the displacement map only.  The normal map does not need the amplitude A, so K2h - a partial
 // wave of latency-bound CTAs when launched alone - runs underneath the store-bound normal-map CTAs instead of in front of
@@ -161,8 +202,9 @@ wso_heights_kernel(const __grid_constant__ Args args) {
 // Every launch carries the programmatic-stream-serialization attribute: the next kernel of the stream is
 // scheduled while this one drains and blocks in griddepcontrol.wait (pdl_wait() at the top of each kernel body)
 // until its predecessor has completed and flushed - stream order is preserved, launch latency is hidden.
-template <class Args, class Kern>
-static cudaError_t launch_pdl(Kern kern, dim3 grid, int threads, int smem, cudaStream_t stream, const Args& args) {
+template <class Args, class Kern, class... Extra>
+static cudaError_t launch_pdl(Kern kern, dim3 grid, int threads, int smem, cudaStream_t stream, const Args& args,
+                              Extra... extra) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = dim3((unsigned)threads, 1, 1);
@@ -173,25 +215,40 @@ static cudaError_t launch_pdl(Kern kern, dim3 grid, int threads, int smem, cudaS
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, args);
+    return cudaLaunchKernelEx(&cfg, kern, args, extra...);
 }
 
 // Which of K1 / K2h / K2 (bits 0 / 1 / 2) of a qualifying batched launch run on the warp-per-line kernels of
 // wso_kernels2.cu.  Default = what measured faster on B200 (profiles/r2_ab_kernel_sets.md): the height pre-pass K2h at
 // 1024^2; everything else stays on the CTA-per-line kernels of this file.  WSO_WARP_CORE overrides the mask for every
 // supported size (0 = none, 7 = all three) - used by the A/B measurements and the parity tests of both kernel sets.
+// Bits 4 / 6 of the same mask: K1 / K2 of the CTA-per-line set in their PERSISTENT form (where a kernel is on the
+// warp-per-line set, that wins).
 static std::atomic<int> g_warp_core_override{-1};  // wso_select_kernels(): -1 = no override
-void set_warp_core_override(int mask) { g_warp_core_override.store(mask < 0 ? -1 : (mask & 7), std::memory_order_relaxed); }
+void set_warp_core_override(int mask) { g_warp_core_override.store(mask < 0 ? -1 : (mask & 0x57), std::memory_order_relaxed); }
 
-static int warp_core_mask(int logn) {
+#ifndef WSO_PERSIST_DEFAULT
+#define WSO_PERSIST_DEFAULT 0
+#endif
+static int kernel_choice_mask(int logn) {
     static const int env_mask = [] {
         const char* env = std::getenv("WSO_WARP_CORE");
-        return env ? (std::atoi(env) & 7) : -1;
+        return env ? (std::atoi(env) & 0x57) : -1;
     }();
     const int forced = g_warp_core_override.load(std::memory_order_relaxed);
-    if (forced >= 0) return forced & 7;
+    if (forced >= 0) return forced & 0x57;
     if (env_mask >= 0) return env_mask;
-    return logn == 10 ? 2 : 0;
+    return (logn == 10 ? 2 : 0) | WSO_PERSIST_DEFAULT;
+}
+static int warp_core_mask(int logn) { return kernel_choice_mask(logn) & 7; }
+
+// CTAs of a persistent kernel = what the device holds at once (queried once per kernel and device)
+template <class Kern>
+static int resident_ctas(Kern kern, int threads, int smem, int dev) {
+    int per_sm = 0, sms = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, (size_t)smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = 148;
+    return per_sm * sms;
 }
 
 // Jacobian mode: K1 (general body, field 1 with its real slot filled), K2h, K2 with four lines per CTA
@@ -265,6 +322,9 @@ static cudaError_t launch_tiled(const Args& args, int n_items, cudaStream_t stre
     const int smem1 = P1::SMEM_BYTES > k1_min ? P1::SMEM_BYTES : k1_min;
     const int smem2 = P2::SMEM_BYTES > k2_min ? P2::SMEM_BYTES : k2_min;
     static std::atomic<bool> configured[16];  // per device: opt in to > 48 KB of dynamic shared memory once
+    // persistent forms: batched launches (the big parameter block) only
+    constexpr bool kPersist = std::is_same<Args, LaunchArgs>::value && (PersistOk<LOGN, TL>::k1 || PersistOk<LOGN, TL>::k2);
+    static int ctas1[16], ctas2[16];  // resident CTAs of the persistent K1 / K2 per device (written before `configured`)
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 16 || !configured[dev].load(std::memory_order_acquire)) {
@@ -277,6 +337,18 @@ static cudaError_t launch_tiled(const Args& args, int n_items, cudaStream_t stre
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(wso_heights_kernel<LOGN, TL, Args>, cudaFuncAttributeMaxDynamicSharedMemorySize, PH::SMEM_BYTES);
         if (e != cudaSuccess) return e;
+        if constexpr (kPersist) {
+            if constexpr (PersistOk<LOGN, TL>::k1) {
+                e = cudaFuncSetAttribute(wso_pass1p_kernel<LOGN, TL, Args>, cudaFuncAttributeMaxDynamicSharedMemorySize, P1::SMEM_BYTES);
+                if (e != cudaSuccess) return e;
+                if (dev >= 0 && dev < 16) ctas1[dev] = resident_ctas(wso_pass1p_kernel<LOGN, TL, Args>, P1::T, P1::SMEM_BYTES, dev);
+            }
+            if constexpr (PersistOk<LOGN, TL>::k2) {
+                e = cudaFuncSetAttribute(wso_pass2p_kernel<LOGN, TL, Args>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2::SMEM_BYTES);
+                if (e != cudaSuccess) return e;
+                if (dev >= 0 && dev < 16) ctas2[dev] = resident_ctas(wso_pass2p_kernel<LOGN, TL, Args>, P2::T, P2::SMEM_BYTES, dev);
+            }
+        }
         if constexpr (K2Split<LOGN, TL>::possible) {
             const int smemnh = K2Split<LOGN, TL>::SMEM > k2_min ? K2Split<LOGN, TL>::SMEM : k2_min;
             e = cudaFuncSetAttribute(wso_pass2nh_kernel<LOGN, TL, Args>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemnh);
@@ -301,7 +373,20 @@ static cudaError_t launch_tiled(const Args& args, int n_items, cudaStream_t stre
     if constexpr (std::is_same<Args, LaunchArgs>::value) {
         if (warp_mask & 1) e = launch_warp_core(LOGN, 0, args, n_items, stream);
     }
-    if (!(warp_mask & 1))
+    int persist = 0;  // bit 0: K1, bit 2: K2 in the persistent form
+    if constexpr (kPersist) {
+        if (fast && dev >= 0 && dev < 16 && k1_min == 0 && k2_min == 0) persist = (kernel_choice_mask(LOGN) >> 4) & 5;
+    }
+    bool k1_done = (warp_mask & 1) != 0;
+    if constexpr (kPersist && PersistOk<LOGN, TL>::k1) {
+        if (!k1_done && (persist & 1)) {
+            const int total = (int)(g1.x * g1.y * g1.z);
+            const int grid = total < ctas1[dev] ? total : ctas1[dev];
+            e = launch_pdl(wso_pass1p_kernel<LOGN, TL, Args>, dim3(grid, 1, 1), P1::T, P1::SMEM_BYTES, stream, args, n_items);
+            k1_done = true;
+        }
+    }
+    if (!k1_done)
         e = fast ? launch_pdl(wso_pass1_kernel<LOGN, TL, Args, true>, g1, P1::T, smem1, stream, args)
                  : launch_pdl(wso_pass1_kernel<LOGN, TL, Args, false>, g1, P1::T, smem1, stream, args);
     if (e != cudaSuccess) return e;
@@ -330,7 +415,16 @@ static cudaError_t launch_tiled(const Args& args, int n_items, cudaStream_t stre
     if constexpr (std::is_same<Args, LaunchArgs>::value) {
         if (warp_mask & 4) e = launch_warp_core(LOGN, 2, args, n_items, stream);
     }
-    if (!(warp_mask & 4)) e = launch_pdl(wso_pass2_kernel<LOGN, TL, Args>, g2, P2::T, smem2, stream, args);
+    bool k2_done = (warp_mask & 4) != 0;
+    if constexpr (kPersist && PersistOk<LOGN, TL>::k2) {
+        if (!k2_done && (persist & 4)) {
+            const int total = (int)(g2.x * g2.y * g2.z);
+            const int grid = total < ctas2[dev] ? total : ctas2[dev];
+            e = launch_pdl(wso_pass2p_kernel<LOGN, TL, Args>, dim3(grid, 1, 1), P2::T, P2::SMEM_BYTES, stream, args, n_items);
+            k2_done = true;
+        }
+    }
+    if (!k2_done) e = launch_pdl(wso_pass2_kernel<LOGN, TL, Args>, g2, P2::T, smem2, stream, args);
     if (e != cudaSuccess) return e;
     if (ev) cudaEventRecord(ev[3], stream);
     return cudaGetLastError();

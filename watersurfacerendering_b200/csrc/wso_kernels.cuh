@@ -333,8 +333,12 @@ struct Pass1 {
         return td.hs + ((size_t)jl * H + i) * 2;
     }
 
+    // the parking space holds the records of ONE row pair: threads that walk a single row pair can always prefetch
+    // (the persistent form does, whatever the size: there the request is a whole store phase ahead of its use)
+    static constexpr bool kPrefetchShape = (IT == H) && (2 * CPT * (int)sizeof(float4) <= kValsPerThread * (int)sizeof(float2));
+    template <bool PF = kPrefetch>
     static WSO_HD void prefetch_thread(const TileDev& td, int bx, int tid, ThreadState& st) {
-        if (!kPrefetch || (!FAST && !td.use_pairs)) return;
+        if (!PF || (!FAST && !td.use_pairs)) return;
         const int i0 = tid % IT, cg = tid / IT;
         if (i0 == 0) return;
 #pragma unroll
@@ -348,7 +352,7 @@ struct Pass1 {
         }
     }
 
-    template <bool TABLE>
+    template <bool TABLE, bool PF = kPrefetch>
     static WSO_HD void evolve_thread(const TileDev& td, const float2* table, float t, int fg, float2* smem, int bx,
                                      int tid, const ThreadState& st) {
         const int i0 = tid % IT, cg = tid / IT;
@@ -368,7 +372,7 @@ struct Pass1 {
         for (int i = i0; i < H; i += IT) {
             if (i == 0) continue;
             float4 q0[CPT], q1[CPT];
-            if (kPrefetch && i == i0) {
+            if (PF && i == i0) {
 #pragma unroll
                 for (int k = 0; k < CPT; ++k) {
                     q0[k] = make_float4(st.v[4 * k + 0].x, st.v[4 * k + 0].y, st.v[4 * k + 1].x, st.v[4 * k + 1].y);
@@ -650,6 +654,11 @@ struct Pass1 {
             });
         }
 
+        split_store(ex, smem, bx, by, bz, args);
+    }
+
+    template <class Exec, class Args>
+    static WSO_HD void split_store(Exec& ex, const float2* smem, int bx, int by, int bz, const Args& args) {
         // ---- split the two real columns, keep m' in [0, N/2), store W[m'][f][slot] ---------------
         // thread -> fixed column pair cp = tid % CP (CP adjacent slots = one 8*CP-byte segment per m'),
         // and (field, m') pairs rest = tid/CP + k*(T/CP)
@@ -708,6 +717,90 @@ struct Pass1 {
             }
         });
     }
+
+    // ---------------------------------------------------------------------------------------------------------
+    // Persistent form (batched launches of the fused tilings): a fixed grid of CTAs walks the work items
+    // w = cta, cta + ncta, ... (w -> column-pair group bx fastest, then field group by, then tile-frame bz).
+    // What a CTA pays once per work item when every item is its own CTA - instruction fetch and parameter loads at
+    // start, the L2 round trip of the records with nothing else to do, the drain of its W stores before the
+    // next CTA can take its place (together a quarter of K1's warp time in the ncu source view of the one-CTA-per-item
+    // kernel, profiles/r2_ncu_c2.txt) - is paid once per CTA here: the records of item w + ncta are requested right
+    // before the split / store phase of item w, into the 16 complex registers that phase does not use, and have
+    // arrived when the next evolve starts.
+    static constexpr bool kPersistOk = FAST && !SLAB && !JAC && ((kFuse0 && kPrefetchF) || (!kFuse0 && kPrefetchShape));
+    template <class Exec, class Args>
+    static WSO_HD void run_persistent(Exec& ex, float2* smem, int cta, int ncta, int n_items, const Args& args) {
+        static_assert(kPersistOk, "persistent K1: a tiling whose threads can park the records of their next item");
+        constexpr int GX = H / CP, GY = 4 / NF;
+        const int total = GX * GY * n_items;
+        float2* table = smem + B * LS;
+        int w = cta;
+        if (w >= total) {  // (the launch sizes the grid <= total)
+            ex.pdl_wait();
+            ex.pdl_release();
+            return;
+        }
+        int bx = w % GX, by = (w / GX) % GY, bz = w / (GX * GY);
+        auto request = [&](int bzr, int bxr) {
+            ex.each([&](int tid, ThreadState& st) {
+                if constexpr (kFuse0) prefetch_fused(args.td[bzr], bxr, tid, st);
+                else prefetch_thread<true>(args.td[bzr], bxr, tid, st);
+            });
+        };
+        request(bz, bx);
+        int table_bz = -1;
+        bool first = true;
+        for (;;) {
+            const TileDev& td = args.td[bz];
+            const float t = args.items[bz].t;
+            // (cos,sin)(omega_j t) of this tile-frame; every thread is past the previous item's evolve (barriers below)
+            if (bz != table_bz) {
+                ex.each([&](int tid, ThreadState&) {
+                    for (int j = tid; j < td.table_len; j += T) {
+                        float sn, cs;
+                        sincos_acc(rmul(rmul((float)j, td.omega0), t), &sn, &cs);
+                        table[j] = make_float2(cs, sn);
+                    }
+                });
+                table_bz = bz;
+            }
+            ex.sync();  // table visible; the previous item's split has finished reading the lines
+            ex.each([&](int tid, ThreadState& st) {
+                if constexpr (kFuse0) fused_thread(td, table, t, by, smem, bx, tid, st);
+                else evolve_thread<true, true>(td, table, t, by, smem, bx, tid, st);
+            });
+            ex.sync();
+            if constexpr (kFuse0) RunStages<LOGN, B, 1, R0, Exec>::run(ex, smem, args.tw);
+            else RunStages<LOGN, B, 0, 1, Exec>::run(ex, smem, args.tw);
+            ex.sync();
+            const int wn = w + ncta;
+            if (first) {  // W of the previous chunk in this lane is still being read until its K2 has completed
+                ex.pdl_wait();
+                first = false;
+            }
+            if (wn >= total) ex.pdl_release();
+            if (bx == 0 && by == 0) {
+                const BatchItem item = args.items[bz];
+                ex.each([&](int tid, ThreadState&) {
+                    if (tid == 0) {
+                        args.minmax[2 * item.slot + 0] = kInitMin;
+                        args.minmax[2 * item.slot + 1] = kInitMax;
+                    }
+                });
+            }
+            int bxn = 0, byn = 0, bzn = 0;
+            if (wn < total) { bxn = wn % GX; byn = (wn / GX) % GY; bzn = wn / (GX * GY); }
+#ifndef WSO_EXP_P_NOAHEAD
+            if (wn < total) request(bzn, bxn);
+#endif
+            split_store(ex, smem, bx, by, bz, args);
+#ifdef WSO_EXP_P_NOAHEAD
+            if (wn < total) request(bzn, bxn);
+#endif
+            if (wn >= total) break;
+            w = wn; bx = bxn; by = byn; bz = bzn;
+        }
+    }
 };
 
 // -------------------------------------------------------------------------------------------------
@@ -765,6 +858,72 @@ struct Pass2 {
     static constexpr bool kReduceFromRegs = HEIGHT_ONLY && Plan<LOGN>::S > 1 && (G % 2 == 0);
 #endif
 
+    // ---- first stage in the paired W layout --------------------------------------------------------------
+    // A thread owns first-stage butterfly PAIRS (p, JN-p) - the mirror column N-n of every column n of butterfly p
+    // belongs to butterfly JN-p - so each 16-byte word (column n, column N-n) feeds one input of each.  Pair 0 is the
+    // two self-mirrored butterflies (0, JN/2); its upper halves are re-slotted exactly as in K1's fused front end.
+    // first_load only requests the words (into the registers the butterflies run in); first_compute runs the
+    // butterflies and stores the stage output: the persistent K2 issues the loads of its NEXT row items ahead of the
+    // pack phase of the current ones.
+    static constexpr int R1st = Plan<LOGN>::R[0];
+    static constexpr int JN1st = N / R1st;
+    static constexpr int NP1st = (2 * R1st <= kValsPerThread) ? kValsPerThread / (2 * R1st) : 1;  // butterfly pairs per thread
+    static WSO_HD void first_load(int tid, ThreadState& st, const float2* Wit, int bx, int by, int crank) {
+        constexpr int R = R1st, JN = JN1st, NP = NP1st;
+        static_assert(!WLayout<LOGN>::paired || (G * NP == JN / 2), "paired first stage: bad shape");
+        const int line = tid / G, lt = tid % G;
+        const int ml = bx * RI + line / LPC;
+        const int f = HEIGHT_ONLY ? 0 : (JAC ? line % LPC : by * 2 + (PAIR ? crank : line % LPC));
+        const float4* src = reinterpret_cast<const float4*>(Wit + ((size_t)ml * 4 + f) * N);
+        static_for<0, NP>([&](auto ic) {
+            constexpr int I = decltype(ic)::value;
+            const int p = lt + G * I;
+            const int base2 = p ? JN - p : JN / 2;
+            float2* v = &st.v[I * 2 * R];  // v[bf*R + idx]
+            static_for<0, R>([&](auto kc) {
+                constexpr int K = decltype(kc)::value;
+                const int n = K < R / 2 ? p + K * JN : base2 + (K - R / 2) * JN;
+                const float4 q = HEIGHT_ONLY ? src[n] : ld_last(src + n);  // K2 is W's last reader
+                constexpr int sa = K < R / 2 ? K : R + (K - R / 2);
+                constexpr int sb = K < R / 2 ? R + (R - 1 - K) : (R - 1 - (K - R / 2));
+                v[sa] = make_float2(q.x, q.y);
+                v[sb] = make_float2(q.z, q.w);
+            });
+        });
+    }
+    static WSO_HD void first_compute(int tid, ThreadState& st, float2* smem) {
+        constexpr int R = R1st, JN = JN1st, NP = NP1st;
+        const int line = tid / G, lt = tid % G;
+        float2* y = smem + line * LS;
+        static_for<0, NP>([&](auto ic) {
+            constexpr int I = decltype(ic)::value;
+            const int p = lt + G * I;
+            const int base2 = p ? JN - p : JN / 2;
+            float2* v = &st.v[I * 2 * R];
+            if (p == 0) {
+                float2 x_hi[R / 2], y_hi[R / 2];
+                static_for<0, R / 2>([&](auto rc) {
+                    constexpr int r = decltype(rc)::value;
+                    x_hi[r] = v[R / 2 + r];
+                    y_hi[r] = v[R + R / 2 + r];
+                });
+                static_for<0, R / 2>([&](auto rc) {
+                    constexpr int r = decltype(rc)::value;
+                    if constexpr (r == 0) v[R / 2] = y_hi[R / 2 - 1];
+                    else v[R / 2 + r] = y_hi[r - 1];
+                    v[R + R / 2 + r] = x_hi[r];
+                });
+            }
+            static_for<0, 2>([&](auto bc) {
+                constexpr int BF = decltype(bc)::value;
+                Dft<R>::run(&v[BF * R]);
+                float2* yb = y + pad_idx((BF == 0 ? p : base2) * R);
+#pragma unroll
+                for (int r = 0; r < R; ++r) yb[r] = v[BF * R + r];
+            });
+        });
+    }
+
     // ---- transform phase: first stage straight from global memory (W rows are contiguous), rest in shared memory
     // crank: rank of this CTA in its cluster pair (PAIR only)
     template <class Exec, class Args>
@@ -781,56 +940,8 @@ struct Pass2 {
         using St = Stage<N, B, R, 1>;
         const int hlog = hl_log(args);
         if constexpr (!SLAB && WLayout<LOGN>::paired) {
-            // Paired layout: a thread owns first-stage butterfly PAIRS (p, JN-p) - the mirror column N-n of every
-            // column n of butterfly p belongs to butterfly JN-p - so each 16-byte word (column n, column N-n) feeds
-            // one input of each.  Pair 0 is the two self-mirrored butterflies (0, JN/2); its upper halves are
-            // re-slotted exactly as in K1's fused front end.
-            constexpr int JN = N / R;
-            constexpr int NP = kValsPerThread / (2 * R);  // butterfly pairs per thread
-            static_assert(NP >= 1 && G * NP == JN / 2, "paired first stage: bad shape");
-            ex.each([&](int tid, ThreadState& st) {
-                const int line = tid / G, lt = tid % G;
-                const int ml = bx * RI + line / LPC;
-                const int f = HEIGHT_ONLY ? 0 : (JAC ? line % LPC : by * 2 + (PAIR ? crank : line % LPC));
-                const float4* src = reinterpret_cast<const float4*>(Wit + ((size_t)ml * 4 + f) * N);
-                float2* y = smem + line * LS;
-                static_for<0, NP>([&](auto ic) {
-                    constexpr int I = decltype(ic)::value;
-                    const int p = lt + G * I;
-                    const int base2 = p ? JN - p : JN / 2;
-                    float2* v = &st.v[I * 2 * R];  // v[bf*R + idx]
-                    static_for<0, R>([&](auto kc) {
-                        constexpr int K = decltype(kc)::value;
-                        const int n = K < R / 2 ? p + K * JN : base2 + (K - R / 2) * JN;
-                        const float4 q = HEIGHT_ONLY ? src[n] : ld_last(src + n);  // K2 is W's last reader
-                        constexpr int sa = K < R / 2 ? K : R + (K - R / 2);
-                        constexpr int sb = K < R / 2 ? R + (R - 1 - K) : (R - 1 - (K - R / 2));
-                        v[sa] = make_float2(q.x, q.y);
-                        v[sb] = make_float2(q.z, q.w);
-                    });
-                    if (p == 0) {
-                        float2 x_hi[R / 2], y_hi[R / 2];
-                        static_for<0, R / 2>([&](auto rc) {
-                            constexpr int r = decltype(rc)::value;
-                            x_hi[r] = v[R / 2 + r];
-                            y_hi[r] = v[R + R / 2 + r];
-                        });
-                        static_for<0, R / 2>([&](auto rc) {
-                            constexpr int r = decltype(rc)::value;
-                            if constexpr (r == 0) v[R / 2] = y_hi[R / 2 - 1];
-                            else v[R / 2 + r] = y_hi[r - 1];
-                            v[R + R / 2 + r] = x_hi[r];
-                        });
-                    }
-                    static_for<0, 2>([&](auto bc) {
-                        constexpr int BF = decltype(bc)::value;
-                        Dft<R>::run(&v[BF * R]);
-                        float2* yb = y + pad_idx((BF == 0 ? p : base2) * R);
-#pragma unroll
-                        for (int r = 0; r < R; ++r) yb[r] = v[BF * R + r];
-                    });
-                });
-            });
+            ex.each([&](int tid, ThreadState& st) { first_load(tid, st, Wit, bx, by, crank); });
+            ex.each([&](int tid, ThreadState& st) { first_compute(tid, st, smem); });
             ex.template sync_group<G, T>(1);
             if constexpr (Plan<LOGN>::S > 1) RunStages<LOGN, B, 1, R, Exec, kReduceFromRegs>::run(ex, smem, args.tw);
             return;
@@ -1056,12 +1167,19 @@ struct Pass2 {
     template <class Exec, class Args>
     static WSO_HD void pack(Exec& ex, const float2* smem, const float2* smem_peer, int bx, int by, int bz, int crank,
                             const Args& args) {
-        const BatchItem item = args.items[bz];
         // Only the displacement map needs K2h's result (disp.y is written already divided by A): the CTAs of the normal
         // map pack right away and fill the device while K2h drains.
         const bool needs_amp = JAC || by == 0;
         if (needs_amp) ex.pdl_wait();
         ex.pdl_release();
+        pack_body(ex, smem, smem_peer, bx, by, bz, crank, args);
+    }
+    // (the caller has waited for K2h where by == 0)
+    template <class Exec, class Args>
+    static WSO_HD void pack_body(Exec& ex, const float2* smem, const float2* smem_peer, int bx, int by, int bz, int crank,
+                                 const Args& args) {
+        const BatchItem item = args.items[bz];
+        const bool needs_amp = JAC || by == 0;
         const float lambda = args.td[bz].lambda;
         const float amp = needs_amp ? amplitude_of(args.minmax[2 * item.slot], args.minmax[2 * item.slot + 1]) : 1.0f;
         const float inv_amp = rdiv(1.0f, amp);
@@ -1117,6 +1235,68 @@ struct Pass2 {
             // the pack phase of a row item reads both of its lines: barrier over that pair of line groups
             ex.template sync_group<GI, T>(1 + (G > 32 ? B : 0));
             pack(ex, smem, nullptr, bx, by, bz, 0, args);
+        }
+    }
+
+    // Persistent form of K2 (batched launches, paired W layout): a fixed grid of CTAs walks the work items
+    // w = cta, cta + ncta, ...; the first half of the item range is the normal map of every tile-frame (needs nothing
+    // from K2h), the second half the displacement map - a CTA reaches its first displacement item, and only there waits
+    // for K2h, after one or two normal-map items.  The W words of item w + ncta are requested before the pack phase of
+    // item w (the 16 complex registers are free there): the L2 round trip that tops the stall list of the one-CTA-per-item
+    // kernel (a third of its warp time, profiles/r2_ncu_c2.txt) overlaps the map stores.
+    template <class Exec, class Args>
+    static WSO_HD void run_persistent(Exec& ex, float2* smem, int cta, int ncta, int n_items, const Args& args) {
+        static_assert(!HEIGHT_ONLY && !SLAB && !PAIR && !JAC && WLayout<LOGN>::paired, "persistent K2: paired layout, maps only");
+        constexpr int GX = H / RI;
+        const int half = GX * n_items, total = 2 * half;
+        int w = cta;
+        if (w >= total) {  // (the launch sizes the grid <= total)
+            ex.pdl_wait();
+            ex.pdl_release();
+            return;
+        }
+        auto decode = [&](int wi, int& bx, int& by, int& bz) {
+            by = wi < half ? 1 : 0;
+            const int rem = wi < half ? wi : wi - half;
+            bz = rem / GX;
+            bx = rem - bz * GX;
+        };
+        int bx, by, bz;
+        decode(w, bx, by, bz);
+        ex.each([&](int tid, ThreadState& st) {
+            first_load(tid, st, args.W + (size_t)bz * ((size_t)H * 4 * N), bx, by, 0);
+        });
+        bool waited = false;
+        for (;;) {
+            ex.each([&](int tid, ThreadState& st) { first_compute(tid, st, smem); });
+            ex.template sync_group<G, T>(1);
+            if constexpr (Plan<LOGN>::S > 1) RunStages<LOGN, B, 1, R1st, Exec, false>::run(ex, smem, args.tw);
+            ex.template sync_group<GI, T>(1 + (G > 32 ? B : 0));
+            const int wn = w + ncta;
+            if (by == 0 && !waited) {
+                ex.pdl_wait();
+                waited = true;
+            }
+            if (wn >= total) ex.pdl_release();
+            int bxn = 0, byn = 0, bzn = 0;
+            if (wn < total) decode(wn, bxn, byn, bzn);
+#ifndef WSO_EXP_P_NOAHEAD
+            if (wn < total)
+                ex.each([&](int tid, ThreadState& st) {
+                    first_load(tid, st, args.W + (size_t)bzn * ((size_t)H * 4 * N), bxn, byn, 0);
+                });
+#endif
+            pack_body(ex, smem, nullptr, bx, by, bz, 0, args);
+#ifdef WSO_EXP_P_NOAHEAD
+            if (wn < total)
+                ex.each([&](int tid, ThreadState& st) {
+                    first_load(tid, st, args.W + (size_t)bzn * ((size_t)H * 4 * N), bxn, byn, 0);
+                });
+#endif
+            if (wn >= total) break;
+            // the lines of a row item are rewritten by the threads of that item only
+            ex.template sync_group<GI, T>(1 + (G > 32 ? B : 0));
+            w = wn; bx = bxn; by = byn; bz = bzn;
         }
     }
 };

@@ -25,7 +25,14 @@ __global__ void __launch_bounds__(Pass1<LOGN, SlabCfg<LOGN>::CP, SlabCfg<LOGN>::
 wso_slab_pass1_kernel(const __grid_constant__ SlabArgs args) {
     extern __shared__ __align__(16) float2 smem[];
     DeviceExec ex;
+    // The field groups of one column-pair block are neighbours in the launch order (blockIdx.x = field group): they read
+    // the same spectrum records, so all but the first find them in L2 (with the column-pair blocks fastest, a rank's
+    // whole share of the records - 268 MB per rank for 16384^2 on 8 devices - lay between two readers of the same record).
+#ifdef WSO_EXP_SLAB_K1_XMAJOR
     Pass1<LOGN, SlabCfg<LOGN>::CP, SlabCfg<LOGN>::NF, true>::run(ex, smem, blockIdx.x, blockIdx.y + args.slab_field0, 0, args);
+#else
+    Pass1<LOGN, SlabCfg<LOGN>::CP, SlabCfg<LOGN>::NF, true>::run(ex, smem, blockIdx.y, blockIdx.x + args.slab_field0, 0, args);
+#endif
 }
 
 template <int LOGN>
@@ -131,7 +138,11 @@ static cudaError_t slab_launch(int phase, const SlabArgs& args, bool pair, int n
         // nfields packed fields from field group args.slab_field0 on (all of them: slab_nfields == 0)
         const int groups = nfields > 0 ? nfields / C::NF : 4 / C::NF;
         if (groups < 1 || (nfields > 0 && nfields % C::NF != 0)) return cudaErrorInvalidValue;
+#ifdef WSO_EXP_SLAB_K1_XMAJOR
         wso_slab_pass1_kernel<LOGN><<<dim3(Hl / C::CP, groups, 1), P1::T, P1::SMEM_BYTES, stream>>>(args);
+#else
+        wso_slab_pass1_kernel<LOGN><<<dim3(groups, Hl / C::CP, 1), P1::T, P1::SMEM_BYTES, stream>>>(args);
+#endif
     } else if (phase == 1) {
         if ((e = opt_in_smem(wso_slab_heights_kernel<LOGN>, PH::SMEM_BYTES)) != cudaSuccess) return e;
         wso_slab_heights_kernel<LOGN><<<dim3(Hl / C::RH, 1, 1), PH::T, PH::SMEM_BYTES, stream>>>(args);
