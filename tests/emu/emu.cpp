@@ -112,7 +112,7 @@ static int run_cfg(const float* amp_t, const float* omega_t, const float* kv, fl
     {   // K2h: height extrema
         std::vector<float2> smem(PH::SMEM_BYTES / sizeof(float2));
         std::vector<ThreadState> st(PH::T);
-        for (int bx = 0; bx < H / RI; ++bx) {
+        for (int bx = 0; bx < PH::grid_x(); ++bx) {
             for (auto& v : smem) v = make_float2(NAN, NAN);
             HostExec ex{PH::T, st.data()};
             PH::run(ex, smem.data(), bx, 0, 0, args);

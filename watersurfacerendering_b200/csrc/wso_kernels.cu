@@ -173,7 +173,7 @@ wso_pass2nh_kernel(const __grid_constant__ Args args) {
         Pass2<LOGN, TL::RI, false>::run(ex, smem, blockIdx.x, 1, blockIdx.z, args);
     } else {
         using PH = typename K2Split<LOGN, TL>::PH;
-        if (blockIdx.x >= PH::H / K2Split<LOGN, TL>::RHS) return;
+        if (blockIdx.x >= PH::grid_x()) return;
         PH::run(ex, smem, blockIdx.x, 0, blockIdx.z, args);
     }
 }
@@ -279,7 +279,7 @@ static cudaError_t launch_tiled_jacobian(const Args& args, int n_items, cudaStre
                        P1::SMEM_BYTES, stream, args);
         if (e != cudaSuccess) return e;
         if (ev) cudaEventRecord(ev[1], stream);
-        e = launch_pdl(wso_heights_kernel<LOGN, TL, Args>, dim3(PH::H / TL::RH, 1, n_items), PH::T, PH::SMEM_BYTES, stream, args);
+        e = launch_pdl(wso_heights_kernel<LOGN, TL, Args>, dim3(PH::grid_x(), 1, n_items), PH::T, PH::SMEM_BYTES, stream, args);
         if (e != cudaSuccess) return e;
         if (ev) cudaEventRecord(ev[2], stream);
         e = launch_pdl(wso_pass2j_kernel<LOGN, Args>, dim3(PJ::H, 1, n_items), PJ::T, PJ::SMEM_BYTES, stream, args);
@@ -404,7 +404,7 @@ static cudaError_t launch_tiled(const Args& args, int n_items, cudaStream_t stre
             return cudaGetLastError();
         }
     }
-    const dim3 gh(PH::H / TL::RH, 1, n_items);
+    const dim3 gh(PH::grid_x(), 1, n_items);
     if constexpr (std::is_same<Args, LaunchArgs>::value) {
         if (warp_mask & 2) e = launch_warp_core(LOGN, 1, args, n_items, stream);
     }

@@ -858,6 +858,31 @@ struct Pass2 {
     static constexpr bool kReduceFromRegs = HEIGHT_ONLY && Plan<LOGN>::S > 1 && (G % 2 == 0);
 #endif
 
+    // K2h, two row items per transform.  The height of row item m' is Re FFT(w), w = its packed-field-0 line; the real
+    // part of a transform is the transform of the conjugate-even part e[n] = (w[n] + conj(w[N-n])) / 2, and the paired W
+    // layout hands a thread w[n] and w[N-n] in ONE 16-byte word.  So one complex transform of e_a + i e_b yields the
+    // heights of row items a (real part) and b (imaginary part): K2h runs half as many lines for one more load per
+    // point.  Line 0 keeps row item 0 alone (rows 0 and N/2 travel as one complex line and need both parts); line
+    // l >= 1 carries the row items 2l-1 and 2l (the last line its single item twice).  The factor 1/2 is applied to the
+    // heights (exact).  Sizes >= 512^2.
+    // Build option, OFF: measured on B200 (profiles/r3_ab_persistent.md) K2h alone gets 14 % faster (1024^2: 3.28 -> 2.81 us,
+    // 2048^2: 13.3 -> 11.5 us per tile-frame) - it is bound by the latency of its loads, not by the transform - and the
+    // whole path does not move (K2h runs underneath K1 / K2 of the other compute lane), while the extrema stop being
+    // bit-identical to the heights K2 writes and to the slab path's.
+#ifdef WSO_EXP_K2H_PAIRS
+    static constexpr bool kTwoForOne = HEIGHT_ONLY && !SLAB && !PAIR && !JAC && WLayout<LOGN>::paired && LOGN >= 9 && kReduceFromRegs;
+#else
+    static constexpr bool kTwoForOne = false;
+#endif
+    static constexpr int kLines = kTwoForOne ? 1 + H / 2 : H;            // K2h / K2 lines groups per tile-frame
+    static WSO_HD constexpr int grid_x() { return (kLines + RI - 1) / RI; }
+    // row items (a, b) of global line gl of the two-for-one K2h (gl >= 1)
+    static WSO_HD void items_of_line(int gl, int& a, int& b) {
+        if (gl > H / 2) gl = H / 2;  // lines past the end of a partially filled CTA repeat the last one
+        a = 2 * gl - 1;
+        b = (2 * gl < H) ? 2 * gl : a;
+    }
+
     // ---- first stage in the paired W layout --------------------------------------------------------------
     // A thread owns first-stage butterfly PAIRS (p, JN-p) - the mirror column N-n of every column n of butterfly p
     // belongs to butterfly JN-p - so each 16-byte word (column n, column N-n) feeds one input of each.  Pair 0 is the
@@ -872,7 +897,39 @@ struct Pass2 {
         constexpr int R = R1st, JN = JN1st, NP = NP1st;
         static_assert(!WLayout<LOGN>::paired || (G * NP == JN / 2), "paired first stage: bad shape");
         const int line = tid / G, lt = tid % G;
-        const int ml = bx * RI + line / LPC;
+        if constexpr (kTwoForOne) {
+            const int gl = bx * RI + line;
+            if (gl != 0) {
+                int ia, ib;
+                items_of_line(gl, ia, ib);
+                const float4* srcA = reinterpret_cast<const float4*>(Wit + ((size_t)ia * 4) * N);
+                const float4* srcB = reinterpret_cast<const float4*>(Wit + ((size_t)ib * 4) * N);
+                static_for<0, NP>([&](auto ic) {
+                    constexpr int I = decltype(ic)::value;
+                    const int p = lt + G * I;
+                    const int base2 = p ? JN - p : JN / 2;
+                    float2* v = &st.v[I * 2 * R];
+                    static_for<0, R>([&](auto kc) {
+                        constexpr int K = decltype(kc)::value;
+                        const int n = K < R / 2 ? p + K * JN : base2 + (K - R / 2) * JN;
+                        const float4 qa = srcA[n], qb = srcB[n];
+                        constexpr int sa = K < R / 2 ? K : R + (K - R / 2);
+                        constexpr int sb = K < R / 2 ? R + (R - 1 - K) : (R - 1 - (K - R / 2));
+                        // 2 e[n] = w[n] + conj(w[N-n]) of both items; x[n] = 2 e_a[n] + i 2 e_b[n], x[N-n] = conj(2 e_a[n]) + i conj(2 e_b[n])
+                        const float ax = qa.x + qa.z, ay = qa.y - qa.w, bx2 = qb.x + qb.z, by2 = qb.y - qb.w;
+                        float2 xn = make_float2(ax - by2, ay + bx2), xm = make_float2(ax + by2, bx2 - ay);
+                        if (K == 0 && n == 0) {  // the word (w[0], w[N/2]): both bins are their own mirrors, e = Re w
+                            xn = make_float2(qa.x + qa.x, qb.x + qb.x);
+                            xm = make_float2(qa.z + qa.z, qb.z + qb.z);
+                        }
+                        v[sa] = xn;
+                        v[sb] = xm;
+                    });
+                });
+                return;
+            }
+        }
+        const int ml = kTwoForOne ? 0 : bx * RI + line / LPC;
         const int f = HEIGHT_ONLY ? 0 : (JAC ? line % LPC : by * 2 + (PAIR ? crank : line % LPC));
         const float4* src = reinterpret_cast<const float4*>(Wit + ((size_t)ml * 4 + f) * N);
         static_for<0, NP>([&](auto ic) {
@@ -986,8 +1043,23 @@ struct Pass2 {
             const bool has_special = (mp0 == 0);                              // CTA-uniform
             ex.each([&](int tid, ThreadState& st) {
                 const int ri = tid / GI, lt = tid % GI;
-                const int mp = mp0 + ri;
-                if (mp != 0) {
+                const int mp = mp0 + ri;   // two-for-one: the global line index (0 = row item 0 alone)
+                if (kTwoForOne && mp != 0) {
+                    int ia, ib;
+                    items_of_line(mp, ia, ib);
+                    // column parity is one value per thread (G and NSL are even); the transform ran on 2 e
+                    const float sa = ((ia + lt) & 1) ? -0.5f : 0.5f, sb = ((ib + lt) & 1) ? -0.5f : 0.5f;
+                    float mn = kInitMin, mx = kInitMax;
+#pragma unroll
+                    for (int k = 0; k < kValsPerThread; ++k) {
+                        const float ha = rmul(st.v[k].x, sa), hb = rmul(st.v[k].y, sb);
+                        mn = ha < mn ? ha : mn;
+                        mx = ha > mx ? ha : mx;
+                        mn = hb < mn ? hb : mn;
+                        mx = hb > mx ? hb : mx;
+                    }
+                    st.v[0] = make_float2(mn, mx);
+                } else if (mp != 0) {
                     // column c = lt + G*i + r*NSL: G and NSL are even, so (-1)^(row+col) is one sign per thread
                     const float s = ((mp + lt) & 1) ? -1.0f : 1.0f;
                     float mn = kInitMin, mx = kInitMax;
