@@ -1,13 +1,13 @@
 #!/bin/bash
-# Dev tool (under gpurun, one GPU): GPU test suite, then A/B of K2h with two row items per transform (in-tree) against the
-# one-item-per-line K2h (variant library all_nopairs) on every workload, and the single-tile latency.   usage: gpu_r3e.sh TAG
+# Dev tool (under gpurun, one GPU): GPU test suite, then A/B of K2 packing from registers (in-tree) against the
+# store-and-reload pack (variant library all_nopackregs) on every workload, and the single-tile latency.   usage: gpu_r3e.sh TAG
 TAG=${1:-r3e}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 timeout 1200 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_gpu.log
 tail -n 3 $OUT/pytest_gpu.log
 B="--steps 5 --warmup 3 --no-cpu-baseline --no-targets"
-V=$PWD/build/variants/libwsocean_all_nopairs.so
+V=$PWD/build/variants/libwsocean_all_notwpre.so
 for m in 0 2; do
   WSO_WARP_CORE=$m timeout 200 python bench.py --workload c2 $B > $OUT/bench_c2_new_m$m.json 2> $OUT/bench_c2_new_m$m.err
   WSO_WARP_CORE=$m WSO_LIB_PATH=$V timeout 200 python bench.py --workload c2 $B > $OUT/bench_c2_old_m$m.json 2> $OUT/bench_c2_old_m$m.err

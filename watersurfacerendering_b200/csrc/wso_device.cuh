@@ -224,8 +224,20 @@ template <> struct Dft<16> {
 // ---------------------------------------------------------------------------------------------
 static constexpr int kValsPerThread = 16;  // complex values a thread carries between barriers
 
+// Twiddle preload (WSO_TW_PRELOAD, default on): the one table value w_{NS*R}^k a thread needs per radix-16 stage depends only on
+// its thread index, so it is requested at the top of the kernel - together with the first global loads - and waits in
+// two or three registers, instead of being requested between a stage's shared-memory loads and its first multiply
+// (where its L1 / L2 round trip showed up as 4-6 % of the warp time of K1 / K2, profiles/r3_ab_persistent.md).
+#ifndef WSO_TW_PRELOAD
+#define WSO_TW_PRELOAD 1
+#endif
+static constexpr bool kTwPreload = WSO_TW_PRELOAD != 0;
+static constexpr int kMaxStages = 4;
+
 struct ThreadState {
     float2 v[kValsPerThread];
+    float2 tw[kMaxStages];  // preloaded twiddle base of stage SI (radix-16 stages behind the first one)
+    float pre[6];           // K1's fused front end: wave numbers requested together with the records (kz of its row pairs, kx of its column pair)
 };
 
 #if defined(__CUDACC__)
@@ -388,6 +400,16 @@ struct Stage {
             Dft<R>::run(&st.v[i * R]);
         }
     }
+    // one butterfly per thread (R == 16) and a preloaded table value
+    static constexpr bool kCanPreload = (NB == 1) && (NS > 1);
+    static WSO_HD float2 twiddle_of(const float2* __restrict__ tw, int tid) {
+        constexpr int tstep = N / (NS * R);
+        return tw[tstep * ((tid % G) % NS)];
+    }
+    static WSO_HD void twiddle_dft_pre(float2 w1, ThreadState& st) {
+        apply_powers<R>(&st.v[0], w1);
+        Dft<R>::run(&st.v[0]);
+    }
 
     // store offsets: element base + r*NS with base = (j/NS)*NS*R + k, k < NS.
     //   NS % 16 == 0 : pad(base + r*NS) = pad(base) + r*(NS + NS/16)
@@ -433,11 +455,22 @@ struct RunStages {
         ex.each([&](int tid, ThreadState& st) { St::load(smem, tid, st); });
         ex.template sync_group<St::G, St::T>(1);
         ex.each([&](int tid, ThreadState& st) {
-            St::twiddle_dft(tw, tid, st);
+            if constexpr (kTwPreload && St::kCanPreload) St::twiddle_dft_pre(st.tw[SI], st);
+            else St::twiddle_dft(tw, tid, st);
             if (!kKeep) St::store(smem, tid, st);
         });
         if (!kKeep) ex.template sync_group<St::G, St::T>(1);
         if constexpr (SI + 1 < Plan<LOGN>::S) RunStages<LOGN, B, SI + 1, NS * R, Exec, KEEP_LAST>::run(ex, smem, tw);
+    }
+    // Requests the table values run() will use (stages SI..S-1); call it early, next to the kernel's first global loads.
+    static WSO_HD void preload(Exec& ex, const float2* __restrict__ tw) {
+        if constexpr (kTwPreload) {
+            constexpr int N = 1 << LOGN;
+            constexpr int R = Plan<LOGN>::R[SI];
+            using St = Stage<N, B, R, NS>;
+            if constexpr (St::kCanPreload) ex.each([&](int tid, ThreadState& st) { st.tw[SI] = St::twiddle_of(tw, tid); });
+            if constexpr (SI + 1 < Plan<LOGN>::S) RunStages<LOGN, B, SI + 1, NS * R, Exec, KEEP_LAST>::preload(ex, tw);
+        }
     }
 };
 

@@ -238,7 +238,8 @@ static int kernel_choice_mask(int logn) {
     const int forced = g_warp_core_override.load(std::memory_order_relaxed);
     if (forced >= 0) return forced & 0x57;
     if (env_mask >= 0) return env_mask;
-    return (logn == 10 ? 2 : 0) | WSO_PERSIST_DEFAULT;
+    (void)logn;  // (round 2, second session: K2h at 1024^2 ran on the warp-per-line set; with the twiddle preload the CTA-per-line K2h is faster again)
+    return WSO_PERSIST_DEFAULT;
 }
 static int warp_core_mask(int logn) { return kernel_choice_mask(logn) & 7; }
 

@@ -501,7 +501,24 @@ struct Pass1 {
             st.v[4 * K + 2] = make_float2(q1.x, q1.y);
             st.v[4 * K + 3] = make_float2(q1.z, q1.w);
         });
+        // ... and the wave numbers the packing multiplies them with (td.kv is a table in global memory: requested here
+        // they arrive with the records instead of after the table barrier)
+        if constexpr (kPrefetchKv) {
+            const int j = td.j0 + jl;
+            static_for<0, R0>([&](auto kc) {
+                constexpr int K = decltype(kc)::value;
+                const int a = K < R0 / 2 ? u + K * JN0 : base2 + (K - R0 / 2) * JN0;
+                st.pre[K] = td.kv[a];
+            });
+            st.pre[4] = td.kv[j];
+            st.pre[5] = td.kv[j ? N - j : 0];
+        }
     }
+#ifdef WSO_EXP_NO_KV_PREFETCH
+    static constexpr bool kPrefetchKv = false;
+#else
+    static constexpr bool kPrefetchKv = kPrefetchF && R0 <= 4;
+#endif
 
     static WSO_HD void fused_thread(const TileDev& td, const float2* table, float t, int fg, float2* smem, int bx,
                                     int tid, ThreadState& st) {
@@ -523,11 +540,11 @@ struct Pass1 {
                     q1[K] = ld_ro(rec + 1);
                 }
             });
-            const float kxA = td.kv[j], kxB = td.kv[N - j];
+            const float kxA = kPrefetchKv ? st.pre[4] : td.kv[j], kxB = kPrefetchKv ? st.pre[5] : td.kv[N - j];
             static_for<0, R0>([&](auto kc) {
                 constexpr int K = decltype(kc)::value;
                 const int a = K < R0 / 2 ? u + K * JN0 : base2 + (K - R0 / 2) * JN0;
-                const float kz = td.kv[a];
+                const float kz = kPrefetchKv ? st.pre[K] : td.kv[a];
                 const float s0 = 0.5f * eval_height<true>(q0[K], table, t);
                 const float s1 = 0.5f * eval_height<true>(q1[K], table, t);
                 static_for<0, NF>([&](auto fc) {
@@ -606,6 +623,8 @@ struct Pass1 {
             if constexpr (kFuse0) prefetch_fused(td, bx, tid, st);
             else prefetch_thread(td, bx, tid, st);
         });
+        if constexpr (kFuse0) RunStages<LOGN, B, 1, R0, Exec>::preload(ex, args.tw);
+        else RunStages<LOGN, B, 0, 1, Exec>::preload(ex, args.tw);
 
         // ---- per-frame (cos,sin)(omega_j * t) table: omega takes few distinct values j*omega0 ------
         float2* table = smem + B * LS;
@@ -748,6 +767,8 @@ struct Pass1 {
             });
         };
         request(bz, bx);
+        if constexpr (kFuse0) RunStages<LOGN, B, 1, R0, Exec>::preload(ex, args.tw);
+        else RunStages<LOGN, B, 0, 1, Exec>::preload(ex, args.tw);
         int table_bz = -1;
         bool first = true;
         for (;;) {
@@ -856,6 +877,22 @@ struct Pass2 {
     static constexpr bool kReduceFromRegs = false;
 #else
     static constexpr bool kReduceFromRegs = HEIGHT_ONLY && Plan<LOGN>::S > 1 && (G % 2 == 0);
+#endif
+
+    // K2 packs from the registers of the last stage.  After the last stage (radix 16: thread j of a line holds X[j + r*N/16],
+    // r < 16) the thread of packed-field line 0 keeps its columns r < 8 and the thread j of line 1 its columns r >= 8; each
+    // hands the OTHER half to its partner through its own shared-memory line (8 stores, one barrier of the row item's
+    // threads, 8 loads) and packs both output rows of its 8 columns - lanes = consecutive columns, 512-byte store
+    // segments as before.  Against "store the whole last stage, barrier, re-load both lines" this is 16 instead of 32
+    // shared-memory accesses per thread (a sixth of K2's; the LSU data pipe is what K2 runs closest to).
+    // Same arithmetic on the same values: bit-identical maps.  Row item 0 (rows 0 and N/2 in one complex line: needs
+    // mirrored columns) keeps the old route.
+    static constexpr int RLast = Plan<LOGN>::R[Plan<LOGN>::S - 1];
+#ifdef WSO_EXP_NO_PACK_REGS
+    static constexpr bool kPackFromRegs = false;
+#else
+    static constexpr bool kPackFromRegs = !HEIGHT_ONLY && !SLAB && !PAIR && !JAC && Plan<LOGN>::S > 1 &&
+                                          RLast == kValsPerThread && G >= 32 && ((N / RLast) % 16 == 0);
 #endif
 
     // K2h, two row items per transform.  The height of row item m' is Re FFT(w), w = its packed-field-0 line; the real
@@ -996,11 +1033,12 @@ struct Pass2 {
         constexpr int R = Plan<LOGN>::R[0];
         using St = Stage<N, B, R, 1>;
         const int hlog = hl_log(args);
+        if constexpr (Plan<LOGN>::S > 1) RunStages<LOGN, B, 1, R, Exec, kReduceFromRegs || kPackFromRegs>::preload(ex, args.tw);
         if constexpr (!SLAB && WLayout<LOGN>::paired) {
             ex.each([&](int tid, ThreadState& st) { first_load(tid, st, Wit, bx, by, crank); });
             ex.each([&](int tid, ThreadState& st) { first_compute(tid, st, smem); });
             ex.template sync_group<G, T>(1);
-            if constexpr (Plan<LOGN>::S > 1) RunStages<LOGN, B, 1, R, Exec, kReduceFromRegs>::run(ex, smem, args.tw);
+            if constexpr (Plan<LOGN>::S > 1) RunStages<LOGN, B, 1, R, Exec, kReduceFromRegs || kPackFromRegs>::run(ex, smem, args.tw);
             return;
         }
         ex.each([&](int tid, ThreadState& st) {
@@ -1027,7 +1065,7 @@ struct Pass2 {
             St::store(smem, tid, st);
         });
         ex.template sync_group<G, T>(1);
-        if constexpr (Plan<LOGN>::S > 1) RunStages<LOGN, B, 1, R, Exec, kReduceFromRegs>::run(ex, smem, args.tw);
+        if constexpr (Plan<LOGN>::S > 1) RunStages<LOGN, B, 1, R, Exec, kReduceFromRegs || kPackFromRegs>::run(ex, smem, args.tw);
     }
 
     // ---- K2h: min/max of the height = Re of packed field 0
@@ -1304,10 +1342,85 @@ struct Pass2 {
         if constexpr (HEIGHT_ONLY) {
             reduce_heights(ex, smem, bx, bz, args);
         } else {
-            // the pack phase of a row item reads both of its lines: barrier over that pair of line groups
-            ex.template sync_group<GI, T>(1 + (G > 32 ? B : 0));
-            pack(ex, smem, nullptr, bx, by, bz, 0, args);
+            if constexpr (kPackFromRegs) {
+                pack_from_regs(ex, smem, bx, by, bz, args);
+            } else {
+                // the pack phase of a row item reads both of its lines: barrier over that pair of line groups
+                ex.template sync_group<GI, T>(1 + (G > 32 ? B : 0));
+                pack(ex, smem, nullptr, bx, by, bz, 0, args);
+            }
         }
+    }
+
+    template <class Exec, class Args>
+    static WSO_HD void pack_from_regs(Exec& ex, float2* smem, int bx, int by, int bz, const Args& args) {
+        constexpr int NSL = N / RLast, HALF = RLast / 2;
+        constexpr int STEP = NSL + (NSL >> 4);  // pad(j + r*NSL) = pad(j) + r*STEP  (NSL % 16 == 0, j < NSL)
+        using StL = Stage<N, B, RLast, NSL>;
+        ex.each([&](int tid, ThreadState& st) {
+            const int line = tid / G, j = tid % G;
+            if (bx * RI + line / 2 == 0) {  // row item 0: whole lines, old route
+                StL::store(smem, tid, st);
+                return;
+            }
+            float2* y = smem + line * LS + pad_idx(j);
+            if ((line & 1) == 0) {
+#pragma unroll
+                for (int r = HALF; r < RLast; ++r) y[r * STEP] = st.v[r];
+            } else {
+#pragma unroll
+                for (int r = 0; r < HALF; ++r) y[r * STEP] = st.v[r];
+            }
+        });
+        ex.template sync_group<GI, T>(1 + (G > 32 ? B : 0));
+        const BatchItem item = args.items[bz];
+        const bool needs_amp = by == 0;
+        if (needs_amp) ex.pdl_wait();
+        ex.pdl_release();
+        const float lambda = args.td[bz].lambda;
+        const float amp = needs_amp ? amplitude_of(args.minmax[2 * item.slot], args.minmax[2 * item.slot + 1]) : 1.0f;
+        const float inv_amp = rdiv(1.0f, amp);
+        if (bx == 0 && by == 0) {
+            ex.each([&](int tid, ThreadState&) {
+                if (tid == 0) args.amp_out[item.slot] = amp;
+            });
+        }
+        float4* out = (by == 0 ? args.disp : args.norm) + (size_t)item.slot * ((size_t)N * N);
+        ex.each([&](int tid, ThreadState& st) {
+            const int line = tid / G, j = tid % G;
+            const int mp = bx * RI + line / 2;
+            float4* outA = out + (size_t)mp * N;
+            float4* outB = out + (size_t)(mp == 0 ? H : N - mp) * N;
+            if (mp == 0) {
+                const float2* l0 = smem + (line & ~1) * LS;
+                pack_item<GI>(l0, l0 + LS, mp, outA, outB, by, lambda, inv_amp, tid % GI, 3);
+                return;
+            }
+            const float2* yp = smem + (line ^ 1) * LS + pad_idx(j);
+            // (-1)^(row+col): the columns j + r*NSL of a thread share the parity of j
+            const float s = ((mp + j) & 1) ? -1.0f : 1.0f;
+            const float sl = rmul(s, lambda);
+            auto emit = [&](int c, float2 a0, float2 a1) {
+                const int cm = (N - c) & (N - 1);  // row N-m' is the conjugate mirror of row m'
+                if (by == 0) {
+                    const float y = rmul(rmul(a0.x, s), inv_amp);
+                    const float x = rmul(sl, a0.y), z = rmul(sl, a1.y);
+                    st_stream(&outA[c], make_float4(x, y, z, 1.0f));
+                    st_stream(&outB[cm], make_float4(-x, y, -z, 1.0f));
+                } else {
+                    const float4 ta = make_float4(s * a0.y, s * a1.y, s * a0.x, s * a1.x);
+                    st_stream(&outA[c], ta);
+                    st_stream(&outB[cm], make_float4(-ta.x, -ta.y, ta.z, ta.w));
+                }
+            };
+            if ((line & 1) == 0) {  // this thread holds packed field 0 (or 2): columns r < HALF
+#pragma unroll
+                for (int r = 0; r < HALF; ++r) emit(j + r * NSL, st.v[r], yp[r * STEP]);
+            } else {                // packed field 1 (or 3): columns r >= HALF
+#pragma unroll
+                for (int r = HALF; r < RLast; ++r) emit(j + r * NSL, yp[r * STEP], st.v[r]);
+            }
+        });
     }
 
     // Persistent form of K2 (batched launches, paired W layout): a fixed grid of CTAs walks the work items
@@ -1335,6 +1448,7 @@ struct Pass2 {
         };
         int bx, by, bz;
         decode(w, bx, by, bz);
+        if constexpr (Plan<LOGN>::S > 1) RunStages<LOGN, B, 1, R1st, Exec, false>::preload(ex, args.tw);
         ex.each([&](int tid, ThreadState& st) {
             first_load(tid, st, args.W + (size_t)bz * ((size_t)H * 4 * N), bx, by, 0);
         });
