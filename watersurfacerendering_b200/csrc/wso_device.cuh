@@ -7,6 +7,7 @@
 #pragma once
 
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #include <cuda_runtime.h>
@@ -256,6 +257,14 @@ struct DeviceExec {
     __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
     __device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+    // 16-byte asynchronous copy global -> shared (cp.async / LDGSTS): no destination registers, completion awaited by
+    // the issuing thread with async_wait() before it - or, behind a barrier, anyone - reads the shared-memory copy.
+    __device__ __forceinline__ void async_copy16(void* smem_dst, const void* gsrc) {
+        const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+    }
+    __device__ __forceinline__ void async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
     // Barrier over the G consecutive threads [g*G, (g+1)*G) that share one FFT line (or line pair), instead of
     // the whole CTA: lines are independent between the evolve / split / pack phases, so a CTA-wide barrier per
     // stage would only make 16 warps wait for the slowest one.  G <= 32: the group lives inside one warp;
@@ -323,6 +332,8 @@ struct HostExec {
     void sync() {}
     void pdl_wait() {}
     void pdl_release() {}
+    void async_copy16(void* smem_dst, const void* gsrc) { memcpy(smem_dst, gsrc, 16); }
+    void async_wait() {}
     template <int G, int T>
     void sync_group(int) {}
     void commit_minmax(float* out) {

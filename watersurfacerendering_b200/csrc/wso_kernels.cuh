@@ -229,7 +229,8 @@ struct Pass1 {
     static constexpr int B = CP * NF;                 // FFT lines per CTA
     static constexpr int T = B * N / kValsPerThread;  // threads per CTA
     static constexpr int LS = LineStride<N>::value;
-    static constexpr int SMEM_BYTES = (B * LS + kMaxTable) * (int)sizeof(float2);
+    // + per column pair the four per-point records of the row pair (0, N/2) (fused front end, see special_request)
+    static constexpr int SMEM_BYTES = (B * LS + kMaxTable) * (int)sizeof(float2) + CP * 4 * (int)sizeof(float4);
     static_assert(T >= 1 && T <= 1024, "bad CTA size");
     static_assert(H % CP == 0 && 4 % NF == 0, "bad tiling");
     // evolve work split: IT threads walk the row pairs i, CG thread groups walk the column pairs
@@ -459,14 +460,21 @@ struct Pass1 {
     // products as evolve_item_general)
     template <bool TABLE>
     static WSO_HD int general_points(const TileDev& td, const float2* table, float t, int i, int jl, Point (&pt)[4]) {
+        const int mA = i, mB = (i == 0) ? H : N - i;
+        const float4* colA = td.h0 + (size_t)jl * 2 * N;
+        const float4* colB = colA + N;
+        const float4 q[4] = {colA[mA], colB[mA], colA[mB], colB[mB]};
+        return general_points_of<TABLE>(td, table, t, i, jl, q, pt);
+    }
+    // ... from records already at hand (q: the four per-point records in the order general_points reads them)
+    template <bool TABLE>
+    static WSO_HD int general_points_of(const TileDev& td, const float2* table, float t, int i, int jl, const float4* q,
+                                        Point (&pt)[4]) {
         const int j = td.j0 + jl;
         const int mA = i, mB = (i == 0) ? H : N - i;
         const int nA = j, nB = (j == 0) ? H : N - j;
         const float kxA = td.kv[nA], kxB = td.kv[nB], kzA = td.kv[mA], kzB = td.kv[mB];
-        const float4* colA = td.h0 + (size_t)jl * 2 * N;
-        const float4* colB = colA + N;
-        const float4 q0 = colA[mA], q1 = colB[mA];
-        const float4 q2 = colA[mB], q3 = colB[mB];
+        const float4 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
         const float h0 = eval_height<TABLE>(q0, table, t), h1 = eval_height<TABLE>(q1, table, t);
         const float h2 = eval_height<TABLE>(q2, table, t), h3 = eval_height<TABLE>(q3, table, t);
         pt[0] = Point{h0, kxA, kzA, rmul(kxA, q0.z), rmul(kzA, q0.z)};
@@ -484,6 +492,33 @@ struct Pass1 {
     template <int FL, int K>
     static constexpr int slot_b() {
         return K < R0 / 2 ? (FL * 2 + 1) * R0 + (R0 - 1 - K) : (FL * 2 + 0) * R0 + (R0 - 1 - (K - R0 / 2));
+    }
+
+    // The row pair (0, N/2) of a column pair goes through the per-point records (four 16-byte loads by the one thread
+    // u == 0) - a dependent L2 round trip in front of the CTA-wide barrier behind the evolve, which held up the other 15
+    // warps of the CTA for 7 % of K1's warp time (profiles/r3_ab_persistent.md).  The thread requests them at the top of
+    // the kernel as asynchronous copies into a 64-byte scratch per column pair (no registers to park them in) and reads
+    // them from there.
+#ifdef WSO_EXP_NO_SPECIAL_ASYNC
+    static constexpr bool kSpecialAsync = false;
+#else
+    static constexpr bool kSpecialAsync = kFuse0;
+#endif
+    static WSO_HD float4* special_scratch(float2* smem) { return reinterpret_cast<float4*>(smem + B * LS + kMaxTable); }
+    template <class Exec>
+    static WSO_HD void special_request(Exec& ex, const TileDev& td, float2* smem, int bx, int tid) {
+        if constexpr (kSpecialAsync) {
+            const int cp = tid / H2, u = tid - cp * H2;
+            if (u != 0) return;
+            const int jl = bx * CP + cp;
+            const float4* colA = td.h0 + (size_t)jl * 2 * N;
+            const float4* colB = colA + N;
+            float4* dst = special_scratch(smem) + cp * 4;
+            ex.async_copy16(dst + 0, colA);      // (m = 0, n = j)
+            ex.async_copy16(dst + 1, colB);      // (0, N-j)
+            ex.async_copy16(dst + 2, colA + H);  // (N/2, j)
+            ex.async_copy16(dst + 3, colB + H);  // (N/2, N-j)
+        }
     }
 
     static WSO_HD void prefetch_fused(const TileDev& td, int bx, int tid, ThreadState& st) {
@@ -570,7 +605,8 @@ struct Pass1 {
             // i = 0 and is replaced by the general one
             if (j != 0) {
                 Point pt[4];
-                const int mask = general_points<true>(td, table, t, 0, jl, pt);
+                const int mask = kSpecialAsync ? general_points_of<true>(td, table, t, 0, jl, special_scratch(smem) + cp * 4, pt)
+                                               : general_points<true>(td, table, t, 0, jl, pt);
                 static_for<0, NF>([&](auto fc) {
                     constexpr int FL = decltype(fc)::value;
                     general_fl<FL>(fg, pt, mask, &out[slot_a<FL, 0>()], &out[slot_b<FL, 0>()]);
@@ -625,6 +661,7 @@ struct Pass1 {
         });
         if constexpr (kFuse0) RunStages<LOGN, B, 1, R0, Exec>::preload(ex, args.tw);
         else RunStages<LOGN, B, 0, 1, Exec>::preload(ex, args.tw);
+        if constexpr (kFuse0) ex.each([&](int tid, ThreadState&) { special_request(ex, td, smem, bx, tid); });
 
         // ---- per-frame (cos,sin)(omega_j * t) table: omega takes few distinct values j*omega0 ------
         float2* table = smem + B * LS;
@@ -637,6 +674,7 @@ struct Pass1 {
                     table[j] = make_float2(c, s);
                 }
             });
+            if constexpr (kFuse0 && kSpecialAsync) ex.each([&](int, ThreadState&) { ex.async_wait(); });
             ex.sync();
         }
 
@@ -766,6 +804,11 @@ struct Pass1 {
                 else prefetch_thread<true>(args.td[bzr], bxr, tid, st);
             });
         };
+        // (the scratch of the special row pair is read during the evolve only: it is rewritten at the loop top, behind
+        // the barriers that follow the previous item's evolve)
+        auto request_special = [&](int bzr, int bxr) {
+            if constexpr (kFuse0) ex.each([&](int tid, ThreadState&) { special_request(ex, args.td[bzr], smem, bxr, tid); });
+        };
         request(bz, bx);
         if constexpr (kFuse0) RunStages<LOGN, B, 1, R0, Exec>::preload(ex, args.tw);
         else RunStages<LOGN, B, 0, 1, Exec>::preload(ex, args.tw);
@@ -775,6 +818,7 @@ struct Pass1 {
             const TileDev& td = args.td[bz];
             const float t = args.items[bz].t;
             // (cos,sin)(omega_j t) of this tile-frame; every thread is past the previous item's evolve (barriers below)
+            request_special(bz, bx);
             if (bz != table_bz) {
                 ex.each([&](int tid, ThreadState&) {
                     for (int j = tid; j < td.table_len; j += T) {
@@ -785,6 +829,7 @@ struct Pass1 {
                 });
                 table_bz = bz;
             }
+            if constexpr (kFuse0 && kSpecialAsync) ex.each([&](int, ThreadState&) { ex.async_wait(); });
             ex.sync();  // table visible; the previous item's split has finished reading the lines
             ex.each([&](int tid, ThreadState& st) {
                 if constexpr (kFuse0) fused_thread(td, table, t, by, smem, bx, tid, st);
