@@ -58,8 +58,8 @@ static int run_cfg(const float* amp_t, const float* omega_t, const float* kv, fl
             const float4 a0 = rec[h0_index(j, i, N, 0)], a3 = rec[h0_index(N - j, N - i, N, 0)];
             const float4 a1 = rec[h0_index(N - j, i, N, 0)], a2 = rec[h0_index(j, N - i, N, 0)];
             if (std::memcmp(&a0.w, &a3.w, 4) != 0 || std::memcmp(&a1.w, &a2.w, 4) != 0) pairs_ok = false;
-            recs[((size_t)j * hN + i) * 2 + 0] = make_float4(a0.x + a3.x, a0.y + a3.y, a0.z, a0.w);
-            recs[((size_t)j * hN + i) * 2 + 1] = make_float4(a1.x + a2.x, a1.y + a2.y, a1.z, a1.w);
+            recs[hs_index((int)j, (int)i, 0, (int)hN)] = make_float4(a0.x + a3.x, a0.y + a3.y, a0.z, a0.w);
+            recs[hs_index((int)j, (int)i, 1, (int)hN)] = make_float4(a1.x + a2.x, a1.y + a2.y, a1.z, a1.w);
         }
     TileDev td;
     td.h0 = rec.data();
@@ -195,8 +195,8 @@ static int run_slab_cfg(int shift, const float* amp_t, const float* omega_t, con
             if (j == 0) continue;
             for (int i = 1; i < H; ++i) {
                 const float4 a0 = record(j, i), a3 = record(N - j, N - i), a1 = record(N - j, i), a2 = record(j, N - i);
-                recs[r][((size_t)jl * H + i) * 2 + 0] = make_float4(a0.x + a3.x, a0.y + a3.y, a0.z, a0.w);
-                recs[r][((size_t)jl * H + i) * 2 + 1] = make_float4(a1.x + a2.x, a1.y + a2.y, a1.z, a1.w);
+                recs[r][hs_index((int)jl, (int)i, 0, (int)H)] = make_float4(a0.x + a3.x, a0.y + a3.y, a0.z, a0.w);
+                recs[r][hs_index((int)jl, (int)i, 1, (int)H)] = make_float4(a1.x + a2.x, a1.y + a2.y, a1.z, a1.w);
             }
         }
         TileDev& td = tds[r];
@@ -335,8 +335,8 @@ static int slab_rank_phase(int shift, int rank, int phase, const float* amp_t, c
             if (j == 0) continue;
             for (int i = 1; i < H; ++i) {
                 const float4 a0 = record(j, i), a3 = record(N - j, N - i), a1 = record(N - j, i), a2 = record(j, N - i);
-                recs[((size_t)jl * H + i) * 2 + 0] = make_float4(a0.x + a3.x, a0.y + a3.y, a0.z, a0.w);
-                recs[((size_t)jl * H + i) * 2 + 1] = make_float4(a1.x + a2.x, a1.y + a2.y, a1.z, a1.w);
+                recs[hs_index((int)jl, (int)i, 0, (int)H)] = make_float4(a0.x + a3.x, a0.y + a3.y, a0.z, a0.w);
+                recs[hs_index((int)jl, (int)i, 1, (int)H)] = make_float4(a1.x + a2.x, a1.y + a2.y, a1.z, a1.w);
             }
         }
     TileDev td;

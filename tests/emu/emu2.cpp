@@ -55,8 +55,8 @@ static bool make_setup(int N, const float* amp_t, const float* omega_t, const fl
             const float4 a0 = s.rec[h0_index(j, i, N, 0)], a3 = s.rec[h0_index(N - j, N - i, N, 0)];
             const float4 a1 = s.rec[h0_index(N - j, i, N, 0)], a2 = s.rec[h0_index(j, N - i, N, 0)];
             if (std::memcmp(&a0.w, &a3.w, 4) != 0 || std::memcmp(&a1.w, &a2.w, 4) != 0) return false;
-            s.recs[((size_t)j * hN + i) * 2 + 0] = make_float4(a0.x + a3.x, a0.y + a3.y, a0.z, a0.w);
-            s.recs[((size_t)j * hN + i) * 2 + 1] = make_float4(a1.x + a2.x, a1.y + a2.y, a1.z, a1.w);
+            s.recs[hs_index((int)j, (int)i, 0, (int)hN)] = make_float4(a0.x + a3.x, a0.y + a3.y, a0.z, a0.w);
+            s.recs[hs_index((int)j, (int)i, 1, (int)hN)] = make_float4(a1.x + a2.x, a1.y + a2.y, a1.z, a1.w);
         }
     s.td.h0 = s.rec.data();
     s.td.hs = s.recs.data();

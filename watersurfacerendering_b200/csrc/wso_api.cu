@@ -407,8 +407,8 @@ int upload_h0(wso_ctx* c, uint32_t tile, const wso_h0_record* h0) {
             const float4 a0 = rec[wso::h0_index((int)j, (int)i, N_, 0)], a3 = rec[wso::h0_index(N_ - (int)j, N_ - (int)i, N_, 0)];
             const float4 a1 = rec[wso::h0_index(N_ - (int)j, (int)i, N_, 0)], a2 = rec[wso::h0_index((int)j, N_ - (int)i, N_, 0)];
             if (std::memcmp(&a0.w, &a3.w, 4) != 0 || std::memcmp(&a1.w, &a2.w, 4) != 0) pairs_ok = false;
-            recs[((size_t)j * hN + i) * 2 + 0] = make_float4(a0.x + a3.x, a0.y + a3.y, a0.z, a0.w);
-            recs[((size_t)j * hN + i) * 2 + 1] = make_float4(a1.x + a2.x, a1.y + a2.y, a1.z, a1.w);
+            recs[wso::hs_index((int)j, (int)i, 0, (int)hN)] = make_float4(a0.x + a3.x, a0.y + a3.y, a0.z, a0.w);
+            recs[wso::hs_index((int)j, (int)i, 1, (int)hN)] = make_float4(a1.x + a2.x, a1.y + a2.y, a1.z, a1.w);
         }
     WSO_CUDA(c, cudaSetDevice(c->device));
     WSO_CUDA(c, cudaStreamSynchronize(c->stream));

@@ -27,9 +27,9 @@ struct TileDev {
     //   w   = quantised dispersion omega (WSTessendorf.h:284-287), or - when table_len > 0 - its integer
     //         multiple j of the base frequency (omega == fl(float(j)*omega0) exactly, checked at Prepare)
     const float4* h0;
-    // [jl][i][2] for column pair j = j0 + jl = (j, N-j) and row pair i = (i, N-i), i in [0, N/2): the same record with
-    // the amplitude replaced by the sum over the mirror pair, h0(k) + h0(-k):
-    //   [0]: k = (m=i, n=j)     [1]: k = (m=i, n=N-j)
+    // [jl][half][i] (hs_index) for column pair j = j0 + jl = (j, N-j) and row pair i = (i, N-i), i in [0, N/2): the same
+    // record with the amplitude replaced by the sum over the mirror pair, h0(k) + h0(-k):
+    //   half 0: k = (m=i, n=j)     half 1: k = (m=i, n=N-j)
     // Only Re FFT is kept, so away from the index-0 / N/2 lines every field depends on h~ only through
     // h~(k) + h~(-k) (same omega for k and -k): one record and one (cos,sin) lookup serve two wave vectors.
     const float4* hs;
@@ -47,6 +47,18 @@ WSO_HD size_t h0_index(int n, int m, int N, int j0) {
     const int j = (n < H) ? n : ((n == H) ? 0 : N - n);
     const int half = (n < H) ? 0 : 1;
     return ((size_t)(j - j0) * 2 + half) * N + m;
+}
+
+// Position of the pair-summed record (row pair i, column pair jl, half) in TileDev::hs.  The two halves of a column pair
+// are separate planes [jl][half][i]: the threads of a warp walk i, so each 16-byte load of a warp is one contiguous
+// 512-byte run (4 cache lines).  Interleaved as [jl][i][2] every load touched 8 lines for the same bytes - 8 of K1's 18
+// global load instructions, a sixth of its L1 wavefronts (profiles/r3_hs_layout.md); -DWSO_EXP_HS_AOS restores that.
+WSO_HD size_t hs_index(int jl, int i, int half, int H) {
+#ifdef WSO_EXP_HS_AOS
+    return ((size_t)jl * H + i) * 2 + half;
+#else
+    return ((size_t)jl * 2 + half) * H + i;
+#endif
 }
 
 struct BatchItem {
@@ -329,9 +341,9 @@ struct Pass1 {
                                       (2 * CPT * (int)sizeof(float4) <= kValsPerThread * (int)sizeof(float2));
 #endif
 
-    static WSO_HD const float4* pair_record(const TileDev& td, int bx, int cg, int k, int i) {
+    static WSO_HD const float4* pair_record(const TileDev& td, int bx, int cg, int k, int i, int half) {
         const int jl = bx * CP + cg + k * CG;
-        return td.hs + ((size_t)jl * H + i) * 2;
+        return td.hs + hs_index(jl, i, half, H);
     }
 
     // the parking space holds the records of ONE row pair: threads that walk a single row pair can always prefetch
@@ -344,8 +356,7 @@ struct Pass1 {
         if (i0 == 0) return;
 #pragma unroll
         for (int k = 0; k < CPT; ++k) {
-            const float4* rec = pair_record(td, bx, cg, k, i0);
-            const float4 a = rec[0], b = rec[1];
+            const float4 a = *pair_record(td, bx, cg, k, i0, 0), b = *pair_record(td, bx, cg, k, i0, 1);
             st.v[4 * k + 0] = make_float2(a.x, a.y);
             st.v[4 * k + 1] = make_float2(a.z, a.w);
             st.v[4 * k + 2] = make_float2(b.x, b.y);
@@ -382,9 +393,8 @@ struct Pass1 {
             } else {
 #pragma unroll
                 for (int k = 0; k < CPT; ++k) {
-                    const float4* rec = pair_record(td, bx, cg, k, i);
-                    q0[k] = rec[0];
-                    q1[k] = rec[1];
+                    q0[k] = *pair_record(td, bx, cg, k, i, 0);
+                    q1[k] = *pair_record(td, bx, cg, k, i, 1);
                 }
             }
             const float kzA = td.kv[i];
@@ -529,8 +539,7 @@ struct Pass1 {
         static_for<0, R0>([&](auto kc) {
             constexpr int K = decltype(kc)::value;
             const int a = K < R0 / 2 ? u + K * JN0 : base2 + (K - R0 / 2) * JN0;
-            const float4* rec = td.hs + ((size_t)jl * H + a) * 2;
-            const float4 q0 = ld_ro(rec), q1 = ld_ro(rec + 1);
+            const float4 q0 = ld_ro(td.hs + hs_index(jl, a, 0, H)), q1 = ld_ro(td.hs + hs_index(jl, a, 1, H));
             st.v[4 * K + 0] = make_float2(q0.x, q0.y);
             st.v[4 * K + 1] = make_float2(q0.z, q0.w);
             st.v[4 * K + 2] = make_float2(q1.x, q1.y);
@@ -570,9 +579,8 @@ struct Pass1 {
                     q1[K] = make_float4(st.v[4 * K + 2].x, st.v[4 * K + 2].y, st.v[4 * K + 3].x, st.v[4 * K + 3].y);
                 } else {
                     const int a = K < R0 / 2 ? u + K * JN0 : base2 + (K - R0 / 2) * JN0;
-                    const float4* rec = td.hs + ((size_t)jl * H + a) * 2;
-                    q0[K] = ld_ro(rec);
-                    q1[K] = ld_ro(rec + 1);
+                    q0[K] = ld_ro(td.hs + hs_index(jl, a, 0, H));
+                    q1[K] = ld_ro(td.hs + hs_index(jl, a, 1, H));
                 }
             });
             const float kxA = kPrefetchKv ? st.pre[4] : td.kv[j], kxB = kPrefetchKv ? st.pre[5] : td.kv[N - j];

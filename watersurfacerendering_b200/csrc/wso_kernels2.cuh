@@ -278,13 +278,12 @@ struct Pass1W {
         float* kvs = reinterpret_cast<float*>(table + kMaxTable + CP * 4);
 
         // ---- pair-summed records of this group's share of the 16 row pairs i = L*a + b of the column pair
-        const float4* rec = td.hs + ((size_t)jl * H + b) * 2;
         float4 q0[RPG], q1[RPG];
 #pragma unroll
         for (int k = 0; k < RPG; ++k) {
             const int a = fg * RPG + k;
-            q0[k] = ld_ro(rec + (size_t)a * L * 2);
-            q1[k] = ld_ro(rec + (size_t)a * L * 2 + 1);
+            q0[k] = ld_ro(td.hs + hs_index(jl, a * L + b, 0, H));
+            q1[k] = ld_ro(td.hs + hs_index(jl, a * L + b, 1, H));
         }
         // ---- per-frame (cos,sin)(omega_j * t) table and the wave numbers -> shared memory
         for (int jj = tid; jj < td.table_len; jj += T) {

@@ -95,14 +95,15 @@ __global__ void __launch_bounds__(256) wso_prepare_kernel(const PrepareArgs a) {
     colB[mA] = q1;
     colA[mB] = q2;
     colB[mB] = q3;
-    float4* rec = a.hs + ((size_t)jl * H + i) * 2;
+    float4* rec0 = a.hs + hs_index(jl, i, 0, H);
+    float4* rec1 = a.hs + hs_index(jl, i, 1, H);
     if (i != 0 && j != 0) {
         // h0(k) + h0(-k): (m,n) mirrors into (N-m, N-n); 1/|k| and the dispersion are even in k
-        rec[0] = make_float4(__fadd_rn(q0.x, q3.x), __fadd_rn(q0.y, q3.y), q0.z, q0.w);
-        rec[1] = make_float4(__fadd_rn(q1.x, q2.x), __fadd_rn(q1.y, q2.y), q1.z, q1.w);
+        *rec0 = make_float4(__fadd_rn(q0.x, q3.x), __fadd_rn(q0.y, q3.y), q0.z, q0.w);
+        *rec1 = make_float4(__fadd_rn(q1.x, q2.x), __fadd_rn(q1.y, q2.y), q1.z, q1.w);
     } else {
-        rec[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-        rec[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        *rec0 = make_float4(0.f, 0.f, 0.f, 0.f);
+        *rec1 = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
 

@@ -120,8 +120,8 @@ int upload_local(wso_slab* s, RecordAt&& record_at) {
             for (uint32_t i = 1; i < H; ++i) {
                 const float4 a0 = cA[i], a3 = cB[n - i], a1 = cB[i], a2 = cA[n - i];
                 if (std::memcmp(&a0.w, &a3.w, 4) != 0 || std::memcmp(&a1.w, &a2.w, 4) != 0) bad[tix] |= 4;
-                recs[((size_t)jl * H + i) * 2 + 0] = make_float4(a0.x + a3.x, a0.y + a3.y, a0.z, a0.w);
-                recs[((size_t)jl * H + i) * 2 + 1] = make_float4(a1.x + a2.x, a1.y + a2.y, a1.z, a1.w);
+                recs[wso::hs_index((int)jl, (int)i, 0, (int)H)] = make_float4(a0.x + a3.x, a0.y + a3.y, a0.z, a0.w);
+                recs[wso::hs_index((int)jl, (int)i, 1, (int)H)] = make_float4(a1.x + a2.x, a1.y + a2.y, a1.z, a1.w);
             }
         }
     };
