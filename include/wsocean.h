@@ -205,6 +205,17 @@ WSO_API int wso_select_kernels(int mask);
  * (tile-frames per launch) the batched calls use, and the CTA tiling of the two transform kernels. */
 WSO_API int wso_get_stats(const wso_ctx* ctx, uint64_t* kernel_launches, uint32_t* chunk);
 
+/* A call that computes ONE tile-frame (wso_compute, wso_compute_async, wso_compute_to_host or wso_compute_batch with
+ * n == 1 - the reference's one ComputeWaves(t) per rendered frame, WaterSurfaceMesh.cpp:123-154) is enqueued as one
+ * launch of an instantiated CUDA graph holding the frame's three kernels, whose parameters are rewritten per call,
+ * instead of three kernel launches.  on = 1 (default): for tile sizes up to 512, where the launches cost more host time
+ * than the kernels take on the device (12.3 instead of 15.6 us per 512^2 frame back to back on B200); larger tiles keep
+ * plain launches, whose programmatic dependent launch overlaps consecutive frames.  on = 2: every size; on = 0: never
+ * (also: environment WSO_FRAME_GRAPH=0|1|2).  The counters say how many frames went out as graph launches and how often
+ * the graph was (re)captured. */
+WSO_API int wso_set_frame_graph(wso_ctx* ctx, int on);
+WSO_API int wso_get_frame_graph_stats(const wso_ctx* ctx, uint64_t* graph_launches, uint64_t* captures);
+
 /* Opt-in per-kernel device timing (the analogue of the reference's VKP_PROFILE_SCOPE table,
  * core/Profile.h:16-32): with profiling on, every launch is bracketed by CUDA events on the compute
  * stream.  wso_get_profile synchronises and returns the accumulated milliseconds of

@@ -183,6 +183,57 @@ def test_batch_matches_single_frames(wso):
         assert_maps_close(ws.copy_map(0, 38), ws.copy_map(1, 38), d_ref, n_ref, "batch frame 36")
 
 
+@pytest.mark.parametrize("n", [64, 512, 2048])
+def test_frame_graph_matches_plain_launches(wso, n):
+    """One ComputeWaves(t) per frame goes out as one CUDA-graph launch (wso_set_frame_graph, wsocean.h): the maps are bit-
+    identical to the three plain launches, the graph is captured once per shape and re-used with new parameters (time,
+    lambda, a re-prepared spectrum), and a change of the tile size captures again."""
+    p, o, xi = _oracle_for(n)
+    times = [0.0, 0.35, 7.125, 12.5]
+    with wso.WSTessendorf(n, p.tile_length) as ws:
+        ws.PrepareWithGauss(xi)
+        ws.set_frame_graph(False)
+        plain = []
+        for t in times:
+            a = ws.ComputeWaves(t)
+            plain.append((a, ws.GetDisplacements().copy(), ws.GetNormals().copy()))
+        assert ws.stats()["frame_graph_launches"] == 0
+        ws.set_frame_graph(True, every_size=True)
+        for rep in range(2):
+            for t, (a0, d0, n0) in zip(times, plain):
+                a = ws.ComputeWaves(t)
+                assert a == a0
+                assert ws.GetDisplacements().tobytes() == d0.tobytes(), (n, t)
+                assert ws.GetNormals().tobytes() == n0.tobytes(), (n, t)
+        st = ws.stats()
+        assert st["frame_graph_captures"] == 1 and st["frame_graph_launches"] >= 2 * len(times) - 1, st
+        _check_frame(ws, o, 3.75, f"graph n={n}")
+        # parameters that live in the kernel arguments: lambda, and a new spectrum in the same buffers
+        ws.SetLambda(-0.5)
+        d_before = ws.GetDisplacements().copy()
+        ws.ComputeWaves(3.75)
+        d_after = ws.GetDisplacements()
+        assert np.array_equal(d_after[..., 1], d_before[..., 1]) and not np.array_equal(d_after[..., 0], d_before[..., 0])
+        ws.SetLambda(p.lam)
+        p2, o2, xi2 = _oracle_for(n, seed=5)
+        ws.PrepareWithGauss(xi2)
+        _check_frame(ws, o2, 1.25, f"graph n={n}, second spectrum")
+        assert ws.stats()["frame_graph_captures"] == 1
+        if n == 64:
+            ws.SetTileSize(128)
+            p3, o3, xi3 = _oracle_for(128)
+            ws.SetTileLength(p3.tile_length)
+            ws.PrepareWithGauss(xi3)
+            for t in (0.5, 2.0, 9.0):
+                _check_frame(ws, o3, t, "graph after a tile size change")
+            assert ws.stats()["frame_graph_captures"] == 2
+        if n == 2048:   # default policy: graph launches up to 512^2 only
+            ws.set_frame_graph(True)
+            before = ws.stats()["frame_graph_launches"]
+            _check_frame(ws, o2, 2.5, "plain launches at 2048")
+            assert ws.stats()["frame_graph_launches"] == before
+
+
 @pytest.mark.parametrize("n", [512, 1024, 2048])
 def test_bulk_tilings_vs_oracle(wso, n):
     """The batched (Bulk) CTA tilings of the benchmarked sizes - K1's fused front end at 512^2 (NF4, radix-2 first

@@ -88,6 +88,8 @@ SYMBOLS = {
     "wso_register_host": (_int, [_vp, C.c_size_t]),
     "wso_unregister_host": (_int, [_vp]),
     "wso_get_stats": (_int, [_vp, C.POINTER(C.c_uint64), C.POINTER(_u32)]),
+    "wso_set_frame_graph": (_int, [_vp, _int]),
+    "wso_get_frame_graph_stats": (_int, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "wso_set_profiling": (_int, [_vp, _int]),
     "wso_get_profile": (_int, [_vp, _vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     # slab-decomposed path (one large grid over several devices)

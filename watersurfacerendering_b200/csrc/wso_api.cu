@@ -68,6 +68,9 @@ struct wso_ctx {
     float* d_kv = nullptr;       // [tile][N]
     float2* d_tw = nullptr;      // [N]
     float2* d_W = nullptr;       // [2][chunk][N/2][4][N]  (double buffered across chunks)
+    wso::FrameGraph frame_graph;  // launch sequence of one tile-frame as an instantiated CUDA graph (wso_launch.h)
+    int frame_graph_mode = 1;     // 0: plain launches, 1: graph for sizes up to 512^2, 2: graph for every size (WSO_FRAME_GRAPH)
+    bool l2_policy_done = false; // WSO_EXP_L2_PERSIST_MB examined (experiment hook in wso_compute_batch)
     float4* d_disp = nullptr;    // [slot][N*N]
     float4* d_norm = nullptr;
     float* d_minmax = nullptr;   // [slot][2]
@@ -246,6 +249,7 @@ void free_device_buffers(wso_ctx* c) {
     cudaFree(c->d_kv); c->d_kv = nullptr;
     cudaFree(c->d_tw); c->d_tw = nullptr;
     cudaFree(c->d_W); c->d_W = nullptr;
+    c->l2_policy_done = false;
     free_map(c, 0);
     free_map(c, 1);
     cudaFree(c->d_minmax); c->d_minmax = nullptr;
@@ -444,6 +448,8 @@ int begin_prepare(wso_ctx* c, uint32_t tile) {
     return WSO_OK;
 }
 
+static constexpr int kFrameGraphMaxLogN = 9;
+
 int enqueue_chunk(wso_ctx* c, uint32_t n_items, const uint32_t* tiles, const float* t, uint32_t first_slot,
                   int wbuf, cudaStream_t stream) {
     LaunchArgs args;
@@ -480,7 +486,14 @@ int enqueue_chunk(wso_ctx* c, uint32_t n_items, const uint32_t* tiles, const flo
     }
     if (c->jacobian && c->logn > wso::kMaxJacobianLogN)
         return fail(c, WSO_ERR_INVALID_ARG, "the Jacobian channel is available for tile sizes up to 4096");
-    cudaError_t e = wso::launch_compute_waves(c->logn, args, (int)n_items, stream, c->jacobian, ev);
+    // a single tile-frame (the reference's one ComputeWaves(t) per rendered frame) goes out as one graph launch
+    // (up to 512^2, where the three launches cost more host time than the kernels take; from 1024^2 on plain launches are
+    // faster back to back - K1 of the next frame overlaps K2 of this one through programmatic dependent launch, which does not
+    // reach across graph launches: profiles/r3_frame_graph.md.  Mode 2 = every size.)
+    const bool as_graph = n_items == 1 && ev == nullptr &&
+                          (c->frame_graph_mode == 2 || (c->frame_graph_mode == 1 && c->logn <= kFrameGraphMaxLogN));
+    cudaError_t e = as_graph ? wso::launch_frame_graph(c->frame_graph, c->logn, args, stream, c->jacobian)
+                             : wso::launch_compute_waves(c->logn, args, (int)n_items, stream, c->jacobian, ev);
     if (e != cudaSuccess) return fail_cuda(c, e, "kernel launch");
     c->first_use = false;
     c->launches += (uint64_t)wso::kernels_per_launch();
@@ -588,6 +601,10 @@ int wso_create(const wso_params* p, int device, uint32_t max_tiles, uint32_t max
         if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess) { rc = fail_cuda(nullptr, e, "cudaStreamCreate"); break; }
         if ((e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) { rc = fail_cuda(nullptr, e, "cudaStreamCreate"); break; }
         if ((e = cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking)) != cudaSuccess) { rc = fail_cuda(nullptr, e, "cudaStreamCreate"); break; }
+        if (const char* env = std::getenv("WSO_FRAME_GRAPH")) {
+            const int v = std::atoi(env);
+            c->frame_graph_mode = v < 0 ? 0 : (v > 2 ? 2 : v);
+        }
         if (const char* env = std::getenv("WSO_LANES")) {  // compute lanes of a batched call (default 2)
             const int v = std::atoi(env);
             if (v >= 1 && v <= 4) c->lanes = v;
@@ -622,6 +639,7 @@ int wso_destroy(wso_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     if (c->aux_stream) cudaStreamSynchronize(c->aux_stream);
+    wso::destroy_frame_graph(c->frame_graph);
     free_device_buffers(c);
     for (int i = 0; i < 2; ++i)
         if (c->ext_sem[i]) cudaDestroyExternalSemaphore(c->ext_sem[i]);
@@ -824,6 +842,38 @@ int wso_compute_batch(wso_ctx* c, uint32_t n, const uint32_t* tiles, const float
     // per-kernel event timing wants the kernels serialised
     const int lanes = c->profiling ? 1 : (int)(n_chunks < (uint32_t)c->lanes ? n_chunks : (uint32_t)c->lanes);
     auto lane_stream = [&](int l) { return l == 0 ? c->stream : (l == 1 ? c->aux_stream : c->more_lanes[l - 2]); };
+    // Experiment hook (WSO_EXP_L2_PERSIST_MB=<carve-out>): the W scratch of every lane as a persisting-L2 access-policy window of
+    // that lane's stream, so that the map stores streaming through L2 do not push W out between K1 and K2.  Measured result in
+    // profiles/r3_memory_instructions.md; off by default.
+    if (!c->l2_policy_done) {
+        c->l2_policy_done = true;
+        if (const char* env = std::getenv("WSO_EXP_L2_PERSIST_MB")) {
+            const long mb = std::atol(env);
+            cudaDeviceProp prop;
+            if (mb > 0 && cudaGetDeviceProperties(&prop, c->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
+                size_t carve = (size_t)mb << 20;
+                if (carve > (size_t)prop.persistingL2CacheMaxSize) carve = (size_t)prop.persistingL2CacheMaxSize;
+                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+                const size_t lane_bytes = (size_t)c->chunk * c->n * c->n * 16;
+                float ratio = 1.0f;
+                if (const char* r = std::getenv("WSO_EXP_L2_PERSIST_RATIO")) ratio = (float)std::atof(r);
+                for (int l = 0; l < (c->lanes > 2 ? c->lanes : 2); ++l) {
+                    cudaStreamAttrValue v = {};
+                    v.accessPolicyWindow.base_ptr = reinterpret_cast<char*>(c->d_W) + (size_t)l * lane_bytes;
+                    size_t win = lane_bytes;
+                    if (win > (size_t)prop.accessPolicyMaxWindowSize) win = (size_t)prop.accessPolicyMaxWindowSize;
+                    v.accessPolicyWindow.num_bytes = win;
+                    v.accessPolicyWindow.hitRatio = ratio;
+                    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                    v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                    cudaStreamSetAttribute(lane_stream(l), cudaStreamAttributeAccessPolicyWindow, &v);
+                }
+                std::fprintf(stderr, "wsocean: persisting L2 carve-out %zu MB (max %d MB), window %zu MB per lane (max %d MB), ratio %.2f\n",
+                             carve >> 20, prop.persistingL2CacheMaxSize >> 20, lane_bytes >> 20, prop.accessPolicyMaxWindowSize >> 20, ratio);
+                cudaGetLastError();
+            }
+        }
+    }
     if (lanes > 1) {
         WSO_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));
         for (int l = 1; l < lanes; ++l) WSO_CUDA(c, cudaStreamWaitEvent(lane_stream(l), c->ev_fork, 0));
@@ -1173,6 +1223,19 @@ int wso_get_profile(wso_ctx* c, double* kernel_ms, uint64_t* launches, uint64_t*
     if (kernel_ms) for (int k = 0; k < 3; ++k) kernel_ms[k] = c->prof_ms[k];
     if (launches) *launches = c->prof_launches;
     if (tile_frames) *tile_frames = c->prof_items;
+    return WSO_OK;
+}
+
+int wso_set_frame_graph(wso_ctx* c, int on) {
+    if (!c) return WSO_ERR_INVALID_ARG;
+    c->frame_graph_mode = on < 0 ? 0 : (on > 2 ? 2 : on);
+    return WSO_OK;
+}
+
+int wso_get_frame_graph_stats(const wso_ctx* c, uint64_t* graph_launches, uint64_t* captures) {
+    if (!c) return WSO_ERR_INVALID_ARG;
+    if (graph_launches) *graph_launches = c->frame_graph.graph_launches;
+    if (captures) *captures = c->frame_graph.captures;
     return WSO_OK;
 }
 

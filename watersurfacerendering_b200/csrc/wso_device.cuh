@@ -107,6 +107,21 @@ WSO_HD float4 ld_last(const float4* p) { return *p; }
 WSO_HD float2 ld_last(const float2* p) { return *p; }
 #endif
 
+// st_keep: K1's stores of the intermediate W, which K2h / K2 read back within the same chunk.  Experiment hook
+// (-DWSO_EXP_W_EVICT_LAST): an L2 evict-last cache hint on the store (createpolicy + st.global.L2::cache_hint).
+#if defined(__CUDA_ARCH__) && defined(WSO_EXP_W_EVICT_LAST)
+WSO_HD void st_keep(float4* p, float4 v) {
+    asm volatile(
+        "{\n\t.reg .b64 pol;\n\t"
+        "createpolicy.fractional.L2::evict_last.b64 pol, 1.0;\n\t"
+        "st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, pol;\n\t}"
+        ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+        : "memory");
+}
+#else
+WSO_HD void st_keep(float4* p, float4 v) { *p = v; }
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // Shared-memory line layout: logical element i of an FFT line lives at pad_idx(i).
 // One float2 of padding per 16 elements makes every access pattern of the Stockham stages below

@@ -202,9 +202,37 @@ wso_heights_kernel(const __grid_constant__ Args args) {
 // Every launch carries the programmatic-stream-serialization attribute: the next kernel of the stream is
 // scheduled while this one drains and blocks in griddepcontrol.wait (pdl_wait() at the top of each kernel body)
 // until its predecessor has completed and flushed - stream order is preserved, launch latency is hidden.
+// (frame graphs, see launch_frame_graph below: while a thread rewrites the parameters of an instantiated graph, the
+// launch code runs as usual and every launch_pdl lands on the graph node of its kernel instead of in the stream)
+struct GraphUpdate {
+    FrameGraph* g;
+    unsigned used;   // nodes rewritten so far (bit per node)
+    bool mismatch;   // a launch for which the graph has no (unused) node: the sequence changed, capture again
+};
+static thread_local GraphUpdate* tl_graph_update = nullptr;
+
 template <class Args, class Kern, class... Extra>
 static cudaError_t launch_pdl(Kern kern, dim3 grid, int threads, int smem, cudaStream_t stream, const Args& args,
                               Extra... extra) {
+    if (GraphUpdate* u = tl_graph_update) {
+        int k = -1;
+        for (int i = 0; i < u->g->n_nodes; ++i)
+            if (u->g->func[i] == reinterpret_cast<void*>(kern)) k = i;
+        if (k < 0 || (u->used >> k & 1u)) {
+            u->mismatch = true;
+            return cudaSuccess;
+        }
+        u->used |= 1u << k;
+        void* params[] = {const_cast<Args*>(&args), static_cast<void*>(&extra)...};
+        cudaKernelNodeParams p = {};
+        p.func = reinterpret_cast<void*>(kern);
+        p.gridDim = grid;
+        p.blockDim = dim3((unsigned)threads, 1, 1);
+        p.sharedMemBytes = (unsigned)smem;
+        p.kernelParams = params;
+        p.extra = nullptr;
+        return cudaGraphExecKernelNodeSetParams(u->g->exec, u->g->node[k], &p);
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = dim3((unsigned)threads, 1, 1);
@@ -472,5 +500,85 @@ cudaError_t launch_compute_waves(int logn, const LaunchArgs& args, int n_items, 
 }
 
 int kernels_per_launch() { return 3; }
+
+void destroy_frame_graph(FrameGraph& g) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (g.graph) cudaGraphDestroy(g.graph);
+    g.exec = nullptr;
+    g.graph = nullptr;
+    g.n_nodes = 0;
+    g.logn = g.jacobian = -1;
+}
+
+// Capture the launch sequence of one tile-frame into g (stream must not be capturing already).  false: not capturable here.
+static bool capture_frame_graph(FrameGraph& g, int logn, const LaunchArgs& args, cudaStream_t stream, bool jacobian) {
+    destroy_frame_graph(g);
+    if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    const cudaError_t le = launch_compute_waves(logn, args, 1, stream, jacobian, nullptr);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(stream, &graph);
+    bool ok = le == cudaSuccess && ce == cudaSuccess && graph != nullptr;
+    size_t n = 0;
+    ok = ok && cudaGraphGetNodes(graph, nullptr, &n) == cudaSuccess && n >= 1 && n <= (size_t)FrameGraph::kMaxNodes;
+    ok = ok && cudaGraphGetNodes(graph, g.node, &n) == cudaSuccess;
+    for (size_t i = 0; ok && i < n; ++i) {
+        cudaGraphNodeType type;
+        cudaKernelNodeParams p = {};
+        ok = cudaGraphNodeGetType(g.node[i], &type) == cudaSuccess && type == cudaGraphNodeTypeKernel &&
+             cudaGraphKernelNodeGetParams(g.node[i], &p) == cudaSuccess;
+        g.func[i] = p.func;
+        for (size_t k = 0; ok && k < i; ++k) ok = g.func[k] != g.func[i];  // nodes are told apart by their kernel
+    }
+    ok = ok && cudaGraphInstantiate(&g.exec, graph, 0) == cudaSuccess;
+    if (!ok) {
+        if (graph) cudaGraphDestroy(graph);
+        g.exec = nullptr;
+        cudaGetLastError();
+        return false;
+    }
+    g.graph = graph;
+    g.n_nodes = (int)n;
+    g.logn = logn;
+    g.jacobian = jacobian ? 1 : 0;
+    g.captures += 1;
+    return true;
+}
+
+cudaError_t launch_frame_graph(FrameGraph& g, int logn, const LaunchArgs& args, cudaStream_t stream, bool jacobian) {
+    // kernels of wso_kernels2.cu (an explicit kernel-set choice) launch through their own helper: plain launches
+    if (g.disabled || (kernel_choice_mask(logn) & 7) != 0) return launch_compute_waves(logn, args, 1, stream, jacobian, nullptr);
+    if (g.warm_logn != logn || g.warm_jacobian != (jacobian ? 1 : 0)) {
+        // first frame of this shape: the plain launch also does the one-time kernel configuration (cudaFuncSetAttribute)
+        const cudaError_t e = launch_compute_waves(logn, args, 1, stream, jacobian, nullptr);
+        if (e == cudaSuccess) {
+            g.warm_logn = logn;
+            g.warm_jacobian = jacobian ? 1 : 0;
+        }
+        return e;
+    }
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        if (!g.exec || g.logn != logn || g.jacobian != (jacobian ? 1 : 0)) {
+            if (!capture_frame_graph(g, logn, args, stream, jacobian)) break;
+            g.graph_launches += 1;
+            return cudaGraphLaunch(g.exec, stream);  // captured with this call's parameters
+        }
+        GraphUpdate u{&g, 0u, false};
+        tl_graph_update = &u;
+        const cudaError_t e = launch_compute_waves(logn, args, 1, stream, jacobian, nullptr);
+        tl_graph_update = nullptr;
+        if (e == cudaSuccess && !u.mismatch && u.used == (1u << g.n_nodes) - 1u) {
+            g.graph_launches += 1;
+            return cudaGraphLaunch(g.exec, stream);
+        }
+        cudaGetLastError();
+        destroy_frame_graph(g);  // another kernel variant serves this frame (e.g. an imported spectrum without the table)
+    }
+    g.disabled = true;
+    destroy_frame_graph(g);
+    return launch_compute_waves(logn, args, 1, stream, jacobian, nullptr);
+}
 
 }  // namespace wso

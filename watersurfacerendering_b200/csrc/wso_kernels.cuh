@@ -773,7 +773,7 @@ struct Pass1 {
                     }
                 } else if constexpr (WLayout<LOGN>::paired) {
                     float4* dst = reinterpret_cast<float4*>(Wit + ((size_t)mp * 4 + f) * N) + jl;
-                    *dst = make_float4(wa.x, wa.y, wb.x, wb.y);
+                    st_keep(dst, make_float4(wa.x, wa.y, wb.x, wb.y));
                 } else {
                     float2* dst = Wit + ((size_t)mp * 4 + f) * N + jl;
                     dst[0] = wa;

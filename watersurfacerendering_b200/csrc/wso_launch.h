@@ -22,6 +22,27 @@ cudaError_t launch_compute_waves(int logn, const LaunchArgs& args, int n_items, 
 static constexpr int kMaxJacobianLogN = 12;
 int kernels_per_launch();
 
+// One tile-frame as a CUDA graph (the reference's calling pattern: one ComputeWaves(t) per rendered frame).  The three
+// launches of a frame cost ~13 us of host enqueue through the runtime - more than the kernels take on the device at 512^2 -
+// so a context keeps the launch sequence of its current (size, jacobian) as an instantiated graph (captured from the very
+// same launch code, programmatic-dependent-launch edges included), rewrites the kernel parameters of its nodes per call
+// (cudaGraphExecKernelNodeSetParams) and pays one cudaGraphLaunch.
+struct FrameGraph {
+    static constexpr int kMaxNodes = 4;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    cudaGraphNode_t node[kMaxNodes] = {};
+    void* func[kMaxNodes] = {};
+    int n_nodes = 0;
+    int logn = -1, jacobian = -1;            // what the instantiated graph was captured for
+    int warm_logn = -1, warm_jacobian = -1;  // a plain launch of this shape has run (one-time kernel configuration done)
+    bool disabled = false;                   // capture or instantiation failed once: plain launches from then on
+    uint64_t graph_launches = 0, captures = 0;
+};
+// args.items[0] = the tile-frame.  Falls back to launch_compute_waves whenever the graph cannot be used.
+cudaError_t launch_frame_graph(FrameGraph& g, int logn, const LaunchArgs& args, cudaStream_t stream, bool jacobian);
+void destroy_frame_graph(FrameGraph& g);
+
 // Warp-per-line kernels (wso_kernels2.cu): 512^2, 1024^2 and 2048^2, every item with the sincos table and the pair-summed
 // records, no Jacobian channel.  which: 0 = K1, 1 = K2h, 2 = K2 (same W layout and stream protocol as the kernels of
 // wso_kernels.cu, so the two sets can be mixed kernel by kernel).

@@ -314,4 +314,12 @@ class WSTessendorf:
     def stats(self):
         k, c = C.c_uint64(), C.c_uint32()
         L.check(self._lib.wso_get_stats(self._h, C.byref(k), C.byref(c)), self._h)
-        return {"kernel_launches": int(k.value), "chunk": int(c.value)}
+        g, r = C.c_uint64(), C.c_uint64()
+        L.check(self._lib.wso_get_frame_graph_stats(self._h, C.byref(g), C.byref(r)), self._h)
+        return {"kernel_launches": int(k.value), "chunk": int(c.value), "frame_graph_launches": int(g.value),
+                "frame_graph_captures": int(r.value)}
+
+    def set_frame_graph(self, on, every_size: bool = False):
+        """Single tile-frame calls as one CUDA-graph launch (default: tile sizes up to 512; every_size: all) or as three
+        plain kernel launches (on = False)."""
+        L.check(self._lib.wso_set_frame_graph(self._h, (2 if every_size else 1) if on else 0), self._h)
