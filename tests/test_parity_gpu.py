@@ -234,6 +234,34 @@ def test_frame_graph_matches_plain_launches(wso, n):
             assert ws.stats()["frame_graph_launches"] == before
 
 
+def test_frame_inside_a_callers_graph_capture(wso):
+    """A caller that captures its own CUDA graph around the per-frame call (stream bound with wso_set_stream) gets the three
+    kernels recorded as plain launches - the library's own frame graph stands aside - and the replay writes the same maps."""
+    import torch
+    n = 256
+    p, o, xi = _oracle_for(n)
+    t = np.array([1.5], np.float32)
+    with wso.WSTessendorf(n, p.tile_length, max_slots=2) as ws:
+        ws.PrepareWithGauss(xi)
+        s = torch.cuda.Stream()
+        ws.set_stream(s.cuda_stream)
+        for _ in range(3):   # plain, capture of the library's own frame graph, graph launch
+            ws.compute_batch(t, first_slot=0)
+        ws.sync()
+        assert ws.stats()["frame_graph_launches"] == 2
+        d_ref, n_ref = ws.copy_map(0, 0), ws.copy_map(1, 0)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            ws.compute_batch(t, first_slot=1)
+        assert ws.stats()["frame_graph_launches"] == 2
+        g.replay()
+        torch.cuda.synchronize()
+        assert ws.copy_map(0, 1).tobytes() == d_ref.tobytes() and ws.copy_map(1, 1).tobytes() == n_ref.tobytes()
+        a_ref, dd, nn = o.compute_waves(1.5)
+        assert_maps_close(ws.copy_map(0, 1), ws.copy_map(1, 1), dd, nn, "frame recorded in a caller's graph")
+        ws.set_stream(None)
+
+
 @pytest.mark.parametrize("n", [512, 1024, 2048])
 def test_bulk_tilings_vs_oracle(wso, n):
     """The batched (Bulk) CTA tilings of the benchmarked sizes - K1's fused front end at 512^2 (NF4, radix-2 first

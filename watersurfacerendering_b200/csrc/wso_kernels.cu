@@ -550,6 +550,12 @@ static bool capture_frame_graph(FrameGraph& g, int logn, const LaunchArgs& args,
 cudaError_t launch_frame_graph(FrameGraph& g, int logn, const LaunchArgs& args, cudaStream_t stream, bool jacobian) {
     // kernels of wso_kernels2.cu (an explicit kernel-set choice) launch through their own helper: plain launches
     if (g.disabled || (kernel_choice_mask(logn) & 7) != 0) return launch_compute_waves(logn, args, 1, stream, jacobian, nullptr);
+    // a caller that is capturing this stream into a graph of its own gets the three kernels recorded as they are
+    cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &capturing) != cudaSuccess || capturing != cudaStreamCaptureStatusNone) {
+        cudaGetLastError();
+        return launch_compute_waves(logn, args, 1, stream, jacobian, nullptr);
+    }
     if (g.warm_logn != logn || g.warm_jacobian != (jacobian ? 1 : 0)) {
         // first frame of this shape: the plain launch also does the one-time kernel configuration (cudaFuncSetAttribute)
         const cudaError_t e = launch_compute_waves(logn, args, 1, stream, jacobian, nullptr);
