@@ -10,17 +10,20 @@
 TAG=${1:-sanitize}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
+# SAN_TOOLS / SAN_CORES / SAN_SEL / SAN_SLAB narrow a run (e.g. a re-check after a kernel change with a small GPU budget)
 SEL='(test_reference_fixtures or test_one_hot_layout or test_batch_matches_single_frames or test_independent_tiles_in_one_batch or (test_all_tile_sizes_vs_oracle and (16 or 32 or 64 or 128 or 256 or 512)) or (test_bulk_tilings_vs_oracle and 512) or (test_jacobian_channel and 64))'
 SLAB='test_slab_world1_fixtures'
+SEL=${SAN_SEL:-$SEL}; SLAB=${SAN_SLAB:-$SLAB}
 rc_all=0
-for tool in memcheck racecheck synccheck; do
-  for core in 0 7; do
+for tool in ${SAN_TOOLS:-memcheck racecheck synccheck}; do
+  for core in ${SAN_CORES:-0 7}; do
     log=$OUT/${tool}_core$core.log
     WSO_WARP_CORE=$core timeout 1500 compute-sanitizer --tool $tool --error-exitcode 77 --print-limit 20 \
       python -m pytest tests/test_parity_gpu.py -m gpu -x -q -k "$SEL" > $log 2>&1
     rc=$?; [ $rc -ne 0 ] && rc_all=1
     echo "$tool core=$core rc=$rc: $(grep -E 'passed|failed|error' $log | tail -n 1) | $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' $log | tail -n 1)"
   done
+  [ "$SLAB" = none ] && continue
   log=$OUT/${tool}_slab.log
   timeout 900 compute-sanitizer --tool $tool --error-exitcode 77 --print-limit 20 \
     python -m pytest tests/test_slab.py -m gpu -x -q -k "$SLAB" > $log 2>&1
