@@ -234,6 +234,31 @@ def test_frame_graph_matches_plain_launches(wso, n):
             assert ws.stats()["frame_graph_launches"] == before
 
 
+def test_imported_spectrum_without_table_and_graph_recapture(wso):
+    """An imported spectrum whose dispersion values are not multiples of one base frequency (nothing Prepare() builds, but
+    wso_import_h0 accepts it) runs on the general K1 body: direct sincosf instead of the per-frame table.  Checked against the
+    oracle fed the same records; the frame graph notices the other kernel variant and captures again, both ways."""
+    n = 128
+    p, o, xi = _oracle_for(n)
+    with wso.WSTessendorf(n, p.tile_length) as ws:
+        ws.set_frame_graph(True, every_size=True)
+        ws.PrepareWithGauss(xi)
+        for t in (0.25, 1.0, 4.5):
+            _check_frame(ws, o, t, "table spectrum")
+        assert ws.stats()["frame_graph_captures"] == 1
+        h0 = o.h0.copy()
+        o.h0["omega"] = (o.h0["omega"] * np.float32(1.37)).astype(np.float32)
+        ws.ImportH0(o.h0)
+        for t in (0.25, 1.0, 4.5):
+            _check_frame(ws, o, t, "spectrum without the table")
+        assert ws.stats()["frame_graph_captures"] == 2
+        o.h0[...] = h0
+        ws.ImportH0(o.h0)
+        for t in (0.5, 2.0):
+            _check_frame(ws, o, t, "table spectrum again")
+        assert ws.stats()["frame_graph_captures"] == 3
+
+
 def test_frame_inside_a_callers_graph_capture(wso):
     """A caller that captures its own CUDA graph around the per-frame call (stream bound with wso_set_stream) gets the three
     kernels recorded as plain launches - the library's own frame graph stands aside - and the replay writes the same maps."""
