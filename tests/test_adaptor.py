@@ -64,6 +64,57 @@ float use(WSTessendorf& m, std::vector<unsigned char>& staging) {
                                str(src2)])
 
 
+REF_CALLER = "/root/reference/src/scene/WaterSurfaceMesh.cpp"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_CALLER), reason="the reference tree exists in the build container only")
+def test_reference_callers_own_expressions_compile_against_the_adaptor(tmp_path):
+    """Not a hand-written list: every `m_ModelTess->...` expression, the constructor call and every `WSTessendorf::` name
+    is cut out of the reference's caller as it lies under /root/reference (WaterSurfaceMesh.cpp) and compiled against the
+    adaptor, with the caller's own variable types (WaterSurfaceMesh.h / .cpp: float times and sliders, glm::vec2 wind,
+    uint32_t sizes) and glm in scope as in the reference build.  The Vulkan / ImGui code around them is not needed for that."""
+    import re
+    src = open(REF_CALLER).read()
+    calls = [m.group(0) for m in re.finditer(r"m_ModelTess->\w+\s*\([^;]*?\)(?:\.data\(\))?(?=\s*[;,)*])", src)]
+    ctor = re.findall(r"m_ModelTess\.reset\(\s*new (WSTessendorf\([^;]*?\))\s*\)\s*;", src)
+    names = sorted(set(re.findall(r"WSTessendorf::(\w+)", src)) | set(re.findall(r"m_ModelTess->(s_k\w+)", src)))
+    members = {c.split("->")[1].split("(")[0].strip() for c in calls}
+    assert {"Prepare", "ComputeWaves", "GetDisplacements", "GetNormals", "SetTileSize", "SetLambda"} <= members
+    assert len(calls) >= 30 and len(ctor) == 1, (len(calls), ctor)
+    body = []
+    for i, c in enumerate(calls):
+        c = " ".join(c.split())
+        body.append(f"    {{ auto&& r{i} = ({c}, 0); (void)r{i}; }}" if re.search(r"->(Set\w+|Prepare)\(", c)
+                    else f"    {{ auto&& r{i} = {c}; (void)r{i}; }}")
+    types = "\n".join(f"    (void)sizeof(WSTessendorf::{n});" for n in names)
+    tu = tmp_path / "ref_calls.cpp"
+    tu.write_text(f"""
+#include <cstdint>
+#include <memory>
+#include <glm/glm.hpp>
+#include "wso_tessendorf_adaptor.hpp"
+void reference_call_sites() {{
+    // the caller's variables (WaterSurfaceMesh.h: m_TimeCtr; WaterSurfaceMesh.cpp:482-483, 804-890)
+    float m_TimeCtr = 0.f, tileLen = 1000.f, windSpeed = 30.f, animPeriod = 200.f, phillipsA = 3.f, damping = 0.1f, lambda = -1.f;
+    glm::vec2 windDir(1.f, 1.f);
+    const uint32_t kNewSize = 256;
+    const uint32_t s_kWSResolutions[7] = {{16, 32, 64, 128, 256, 512, 1024}};
+    int tileRes = 5;
+    const auto kSampleCount = WSTessendorf::s_kDefaultTileSize;
+    const auto kWaveLength = WSTessendorf::s_kDefaultTileLength;
+    std::unique_ptr<WSTessendorf> m_ModelTess;
+    m_ModelTess.reset(new {ctor[0]});
+{chr(10).join(body)}
+{types}
+    const glm::vec4* d = m_ModelTess->GetDisplacements().data();   // what vkp::Buffer::CopyToMapped receives (cpp:728, 741)
+    const glm::vec4* n = m_ModelTess->GetNormals().data();
+    (void)d; (void)n;
+}}
+""")
+    subprocess.check_call([GXX, "-std=c++17", "-fsyntax-only", "-Wall", "-I", "/root/reference/libs/glm", "-I",
+                           os.path.join(ROOT, "include"), str(tu)])
+
+
 @pytest.mark.gpu
 def test_frame_loop_matches_python_path():
     exe = _build_frame_loop()
