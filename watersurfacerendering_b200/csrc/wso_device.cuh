@@ -297,6 +297,21 @@ struct DeviceExec {
         }
     }
 
+    // Producer / consumer barrier per column pair, behind K1's fused front end.  There the H2 threads [cp*H2, (cp+1)*H2) write
+    // the first-stage output of the NF lines of column pair cp, and the next stage reads line l with the G threads [l*G, (l+1)*G)
+    // (lines l = fl*CP + cp): every thread announces its writes on its producer column pair (bar.arrive) and waits on the
+    // column pair of the line it reads next (bar.sync); a column pair whose four warps are done moves on while the others
+    // still evolve, instead of all warps of the CTA meeting at __syncthreads().
+    template <int CP, int NF, int H2, int G>
+    __device__ __forceinline__ void sync_colpair(int id_base) {
+        static_assert(H2 % 32 == 0 && G % 32 == 0, "whole warps on both sides");
+        constexpr int COUNT = H2 + NF * G;  // arrivals + waiters per column pair
+        const int idp = id_base + (int)threadIdx.x / H2;
+        const int idc = id_base + ((int)threadIdx.x / G) % CP;
+        asm volatile("bar.arrive %0, %1;" ::"r"(idp), "n"(COUNT) : "memory");
+        asm volatile("bar.sync %0, %1;" ::"r"(idc), "n"(COUNT) : "memory");
+    }
+
     // Fold the (min,max) every thread left in st.v[0] into out[0] (min) / out[1] (max): warp-shuffle butterfly,
     // one partial per warp through shared memory, then ONE pair of atomics per CTA (all CTAs of a tile-frame hit the
     // same two words, and same-address atomics serialise in one L2 slice).  Float ordering through the sign-aware
@@ -351,6 +366,8 @@ struct HostExec {
     void async_wait() {}
     template <int G, int T>
     void sync_group(int) {}
+    template <int CP, int NF, int H2, int G>
+    void sync_colpair(int) {}
     void commit_minmax(float* out) {
         for (int t = 0; t < nthreads; ++t) {
             if (states[t].v[0].x < out[0]) out[0] = states[t].v[0].x;

@@ -434,6 +434,15 @@ struct Pass1 {
     static constexpr bool kFuse0 = FAST && Plan<LOGN>::S > 1 && NF * R0 == 8 && H2 >= 2 && T == CP * H2;
 #endif
     static constexpr bool kPrefetchF = kFuse0 && 4 * R0 <= kValsPerThread;  // all 2*R0 records fit the parking space
+    // barrier behind the fused front end per column pair instead of CTA-wide (DeviceExec::sync_colpair); the named barriers
+    // 1..B belong to the lines when a line is more than one warp
+    static constexpr int kColPairIdBase = (N / kValsPerThread > 32) ? 1 + B : 1;
+#ifdef WSO_EXP_NO_COLPAIR_SYNC
+    static constexpr bool kColPairSync = false;
+#else
+    static constexpr bool kColPairSync = kFuse0 && CP > 1 && H2 % 32 == 0 && (N / kValsPerThread) % 32 == 0 &&
+                                         kColPairIdBase + CP - 1 <= 15;
+#endif
 
     // packed field in line slot FL of field group fg: F = fg*NF + FL (fg is CTA-uniform)
     template <int FL>
@@ -694,7 +703,8 @@ struct Pass1 {
             else if constexpr (!FAST) evolve_thread<false>(td, table, t, by, smem, bx, tid, st);
         });
 #endif
-        ex.sync();
+        if constexpr (kColPairSync) ex.template sync_colpair<CP, NF, H2, N / kValsPerThread>(kColPairIdBase);
+        else ex.sync();
 
         // ---- B complex FFTs of length N along m ---------------------------------------------------
 #ifndef WSO_EXP_SKIP_FFT1
