@@ -437,6 +437,19 @@ struct Pass1 {
     // barrier behind the fused front end per column pair instead of CTA-wide (DeviceExec::sync_colpair); the named barriers
     // 1..B belong to the lines when a line is more than one warp
     static constexpr int kColPairIdBase = (N / kValsPerThread > 32) ? 1 + B : 1;
+    // split + store dealt to the field groups, with a barrier per field group in front of it (split_store)
+    static constexpr int kFieldIdBase = kColPairIdBase + CP;
+#ifdef WSO_EXP_NO_FIELD_SPLIT
+    static constexpr bool kFieldSplit = false;
+#else
+    // (measured per size, profiles/r3_memory_instructions.md section 9: 2048^2 K1 -3 %, 512^2 batches -2 %, but the 1024^2 path
+    // 0.45 % slower in four pairs of runs although K1 alone is equal - that size keeps the CTA-wide barrier)
+#ifndef WSO_TUNE_FIELD_SPLIT_SKIP_LOGN
+#define WSO_TUNE_FIELD_SPLIT_SKIP_LOGN 10
+#endif
+    static constexpr bool kFieldSplit = !SLAB && NF > 1 && (T / NF) % 32 == 0 && (T / NF) % CP == 0 && H % (T / NF / CP) == 0 &&
+                                        kFieldIdBase + NF - 1 <= 15 && LOGN != WSO_TUNE_FIELD_SPLIT_SKIP_LOGN;
+#endif
 #ifdef WSO_EXP_NO_COLPAIR_SYNC
     static constexpr bool kColPairSync = false;
 #else
@@ -711,7 +724,10 @@ struct Pass1 {
         if constexpr (kFuse0) RunStages<LOGN, B, 1, R0, Exec>::run(ex, smem, args.tw);  // stage 0 ran in registers
         else RunStages<LOGN, B, 0, 1, Exec>::run(ex, smem, args.tw);
 #endif
-        ex.sync();  // the split below reads CP lines per work item
+        // the split below reads the CP lines of a packed field per work item: with the split dealt to the field groups
+        // (kFieldSplit) only the T/NF threads that own those lines have to meet, otherwise the whole CTA
+        if constexpr (kFieldSplit) ex.template sync_group<T / NF, T>(kFieldIdBase);
+        else ex.sync();
 #ifdef WSO_EXP_SKIP_STORE1
         if (args.W != nullptr) return;
 #endif
@@ -740,18 +756,23 @@ struct Pass1 {
         // The sweep structure is compile-time: SWEEPS = 8 fully unrolled iterations (all shared-memory loads of a thread
         // are in flight together; a rolled loop paid one LDS round trip and ~20 index instructions per iteration -
         // 22 % of K1's executed instructions in profiles/r1h_ncu_c2.txt).
+        // kFieldSplit: the T/NF threads that transformed the lines of packed field fl (threads [fl*T/NF, (fl+1)*T/NF)) also
+        // split and store that field, so the barrier in front of the split is theirs alone (run()); otherwise every thread
+        // walks all NF fields.  Same number of sweeps per thread, same store segments either way.
         float2* Wit = args.W + (size_t)bz * ((size_t)H * 4 * N);
-        constexpr int STEP = T / CP;             // (field, m') pairs covered per sweep of the CTA
-        constexpr int SWEEPS = NF * H / STEP;    // = 8
-        constexpr int PER_LINE = H / STEP;       // sweeps per packed field
-        static_assert(STEP >= 1 && H % STEP == 0 && SWEEPS * STEP == NF * H, "bad split tiling");
+        constexpr int TG = kFieldSplit ? T / NF : T;   // threads that share the split of one field (or of all)
+        constexpr int STEP = TG / CP;                  // m' values covered per sweep
+        constexpr int PER_LINE = H / STEP;             // sweeps per packed field
+        constexpr int SWEEPS = (kFieldSplit ? 1 : NF) * PER_LINE;  // = 8
+        static_assert(STEP >= 1 && H % STEP == 0 && SWEEPS * STEP * (kFieldSplit ? NF : 1) == NF * H, "bad split tiling");
         ex.each([&](int tid, ThreadState&) {
-            const int cp = tid % CP;
+            const int tl = tid % TG;
+            const int cp = tl % CP;
             const int jl = bx * CP + cp;
-            const int b = tid / CP;              // m' of the first sweep, < STEP
+            const int b = tl / CP;               // m' of the first sweep, < STEP
 #pragma unroll
             for (int k = 0; k < SWEEPS; ++k) {
-                const int fl = k / PER_LINE;
+                const int fl = kFieldSplit ? tid / TG : k / PER_LINE;
                 const int mp = b + (k % PER_LINE) * STEP;
                 const float2* line = smem + (fl * CP + cp) * LS;
                 const float2 c1 = line[pad_idx(mp)];
